@@ -1,0 +1,584 @@
+// HBM-bound kernels of the predictor-corrector step: noise draws, unit-cell wrap, coordinate / lattice
+// update, atom-type (D3PM) update, RePaint overwrite, wrapped-Gaussian score, segment reductions.
+// Reference functions are cited next to each kernel (paths relative to the reference package).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace b200md {
+
+// -------------------------------------------------------------------------------------------------
+// Noise draws.  One thread per Philox block (4 values).
+// -------------------------------------------------------------------------------------------------
+enum DrawKind { kNormal = 0, kUniform = 1, kGumbel = 2 };
+
+template <int KIND>
+__global__ void draw_kernel(float* __restrict__ out, int64_t n_samples, int32_t units, int32_t unit_size,
+                            float small_epsilon, uint64_t seed, uint32_t step_id, uint32_t draw_id,
+                            uint64_t sample_offset) {
+  const int32_t blocks_per_unit = (unit_size + 3) >> 2;
+  const int64_t per_sample = (int64_t)units * blocks_per_unit;
+  const int64_t total = n_samples * per_sample;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = t / per_sample;
+    const int64_t r = t - s * per_sample;
+    const int32_t unit = (int32_t)(r / blocks_per_unit);
+    const int32_t blk = (int32_t)(r - (int64_t)unit * blocks_per_unit);
+    Philox4 p = draw_block(seed, sample_offset + (uint64_t)s, (uint32_t)r, step_id, draw_id);
+    float v[4];
+    if (KIND == kNormal) {
+      normal4(p, v);
+    } else {
+      v[0] = u01(p.x); v[1] = u01(p.y); v[2] = u01(p.z); v[3] = u01(p.w);
+      if (KIND == kGumbel) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = gumbel_from_uniform(v[i], small_epsilon);
+      }
+    }
+    float* o = out + (s * units + unit) * (int64_t)unit_size + blk * 4;
+    const int n = min(4, unit_size - blk * 4);
+    for (int i = 0; i < n; ++i) o[i] = v[i];
+  }
+}
+
+template <int KIND>
+static int launch_draw(float* out, int64_t n_samples, int32_t units, int32_t unit_size, float eps,
+                       uint64_t seed, uint32_t step_id, uint32_t draw_id, uint64_t sample_offset,
+                       b200md_stream_t stream) {
+  if (!out || n_samples < 0 || units <= 0 || unit_size <= 0) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0) return B200MD_OK;
+  int64_t total = n_samples * (int64_t)units * ((unit_size + 3) / 4);
+  int threads = 256;
+  int64_t blocks = ceil_div64(total, threads);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  draw_kernel<KIND><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+      out, n_samples, units, unit_size, eps, seed, step_id, draw_id, sample_offset);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// map_relative_coordinates_to_unit_cell   utils/basis_transformations.py:95-119
+// -------------------------------------------------------------------------------------------------
+__global__ void wrap_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = wrap_unit(x[i]);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Coordinate update, generators/langevin_generator.py:194-200:
+//   updated = (x + (score_weight * s) / sigma) + noise_weight * z ; wrap
+// One thread per atom.  Rounding chain kept explicit (no FMA contraction).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pc_update_value(float x, float s, float z, float sw, float sigma,
+                                                 float nw) {
+  float a = __fdiv_rn(__fmul_rn(sw, s), sigma);
+  float b = __fmul_rn(nw, z);
+  return wrap_unit(__fadd_rn(__fadd_rn(x, a), b));
+}
+
+template <int D>
+__global__ void pc_coordinates_update_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                             const float* __restrict__ z, float sw, float sigma,
+                                             float nw, int64_t n_samples, int32_t n_atoms,
+                                             uint64_t seed, uint32_t step_id,
+                                             uint64_t sample_offset, float* __restrict__ out) {
+  const int64_t total = n_samples * n_atoms;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    float zz[4];
+    if (z != nullptr) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) zz[d] = z[t * D + d];
+    } else {
+      const int64_t smp = t / n_atoms;
+      const int32_t atom = (int32_t)(t - smp * n_atoms);
+      Philox4 p = draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)atom, step_id,
+                             B200MD_DRAW_COORD_NORMAL);
+      normal4(p, zz);
+    }
+    float xv[D], sv[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { xv[d] = x[t * D + d]; sv[d] = s[t * D + d]; }
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[t * D + d] = pc_update_value(xv[d], sv[d], zz[d], sw, sigma, nw);
+  }
+}
+
+// Lattice update, generators/langevin_generator.py:485-490 (no wrap).  One thread per (sample, 3-block).
+__global__ void pc_lattice_update_kernel(const float* __restrict__ l, const float* __restrict__ s,
+                                         const float* __restrict__ z, float sw, float sigma_n, float nw,
+                                         int64_t n_samples, int32_t n_lp, uint64_t seed,
+                                         uint32_t step_id, uint64_t sample_offset,
+                                         float* __restrict__ out) {
+  const int32_t units = (n_lp + 2) / 3;
+  const int64_t total = n_samples * units;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t smp = t / units;
+    const int32_t unit = (int32_t)(t - smp * units);
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (z == nullptr) {
+      Philox4 p = draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)unit, step_id,
+                             B200MD_DRAW_LATTICE_NORMAL);
+      normal4(p, zz);
+    }
+    for (int d = 0; d < 3; ++d) {
+      int c = unit * 3 + d;
+      if (c >= n_lp) break;
+      int64_t i = smp * n_lp + c;
+      float zv = (z != nullptr) ? z[i] : zz[d];
+      float a = __fdiv_rn(__fmul_rn(sw, s[i]), sigma_n);
+      out[i] = __fadd_rn(__fadd_rn(l[i], a), __fmul_rn(nw, zv));
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Atom-type update.  One CTA per sample (per-sample reductions: all-MASK flag, arg-max over atoms).
+//   generators/langevin_generator.py:247-439, utils/d3pm_utils.py:64-150
+// -------------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 32;
+
+__global__ void atom_types_update_kernel(const float* __restrict__ logits, const int64_t* __restrict__ a_in,
+                                         const float* __restrict__ q, const float* __restrict__ qbar,
+                                         const float* __restrict__ qbar_tm1,
+                                         const float* __restrict__ gumbel, const float* __restrict__ binary,
+                                         int32_t flags, float eps, int32_t n_atoms, int32_t C,
+                                         uint64_t seed, uint32_t step_id, uint64_t sample_offset,
+                                         int64_t* __restrict__ a_out, float* __restrict__ probs_out,
+                                         int32_t* __restrict__ status) {
+  extern __shared__ unsigned char smem_raw[];
+  float* s_q = reinterpret_cast<float*>(smem_raw);  // [3][C*C]
+  float* s_best = s_q + 3 * C * C;                  // [n_atoms]  winning Gumbel value
+  int32_t* s_new = reinterpret_cast<int32_t*>(s_best + n_atoms);  // [n_atoms] sampled type
+  __shared__ int s_not_all_masked;
+  __shared__ float s_red_val[32];
+  __shared__ int s_red_idx[32];
+
+  const int64_t smp = blockIdx.x;
+  const int mask_class = C - 1;
+  const bool greedy = flags & B200MD_ATOM_GREEDY;
+  const bool one_transition = (flags & B200MD_ATOM_ONE_TRANSITION) != 0;
+  const bool last_step = (flags & B200MD_ATOM_LAST_STEP) != 0;
+
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    s_q[i] = q[i]; s_q[C * C + i] = qbar[i]; s_q[2 * C * C + i] = qbar_tm1[i];
+  }
+  if (threadIdx.x == 0) s_not_all_masked = 0;
+  __syncthreads();
+  const int64_t* a_row = a_in + smp * n_atoms;
+  if (greedy) {
+    int any = 0;
+    for (int n = threadIdx.x; n < n_atoms; n += blockDim.x) any |= (a_row[n] != mask_class);
+    if (any) s_not_all_masked = 1;  // benign race: all writers store 1
+  }
+  __syncthreads();
+  const bool all_masked = (s_not_all_masked == 0);
+  unsigned local_status = 0;
+
+  for (int n = threadIdx.x; n < n_atoms; n += blockDim.x) {
+    const int64_t node = smp * n_atoms + n;
+    const int at = (int)a_row[n];
+    float p0[kMaxClasses];
+    // softmax -> clip -> renormalise   utils/d3pm_utils.py:140-149
+    float mx = -CUDART_INF_F;
+    for (int c = 0; c < C; ++c) { p0[c] = logits[node * C + c]; mx = fmaxf(mx, p0[c]); }
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) { p0[c] = expf(p0[c] - mx); sum += p0[c]; }
+    float check = 0.f;
+    for (int c = 0; c < C; ++c) { p0[c] = p0[c] / sum; check += p0[c]; }
+    if (!(fabsf(check - 1.0f) <= 1e-5f + 1.3e-6f)) local_status |= B200MD_STATUS_BAD_LOGITS;
+    float csum = 0.f;
+    for (int c = 0; c < C; ++c) { p0[c] = fmaxf(p0[c], eps); csum += p0[c]; }
+    for (int c = 0; c < C; ++c) p0[c] = p0[c] / csum;
+    // p(a_{t-1} | a_t)   utils/d3pm_utils.py:102-124
+    float den = 0.f;
+    for (int j = 0; j < C; ++j) den += p0[j] * s_q[C * C + j * C + at];
+    float prob[kMaxClasses];
+    for (int i = 0; i < C; ++i) {
+      float num1 = 0.f;
+      for (int j = 0; j < C; ++j) num1 += p0[j] * s_q[2 * C * C + j * C + i];
+      float num2 = s_q[i * C + at];
+      prob[i] = (num1 * num2) / den;
+    }
+    // Gumbel noise
+    float gum[kMaxClasses];
+    if (gumbel != nullptr) {
+      for (int c = 0; c < C; ++c) gum[c] = gumbel[node * C + c];
+    } else {
+      const int nblk = (C + 3) >> 2;
+      for (int b = 0; b < nblk; ++b) {
+        Philox4 p = draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)(n * nblk + b), step_id,
+                               B200MD_DRAW_GUMBEL);
+        float u[4] = {u01(p.x), u01(p.y), u01(p.z), u01(p.w)};
+        for (int i = 0; i < 4 && b * 4 + i < C; ++i) gum[b * 4 + i] = gumbel_from_uniform(u[i], eps);
+      }
+    }
+    if (greedy) {
+      // generators/langevin_generator.py:382-439
+      float bin;
+      if (binary != nullptr) {
+        bin = binary[node];
+      } else {
+        Philox4 p = draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)n, step_id,
+                               B200MD_DRAW_BINARY);
+        bin = u01(p.x);
+      }
+      const bool do_greedy = (!all_masked) && (bin > prob[mask_class]) && (at == mask_class);
+      if (do_greedy) prob[mask_class] = 0.f;
+      if (!all_masked)
+        for (int c = 0; c < C; ++c) gum[c] = 0.f;
+    }
+    if (probs_out != nullptr)
+      for (int c = 0; c < C; ++c) probs_out[node * C + c] = prob[c];
+    float best = -CUDART_INF_F;
+    int best_c = 0;
+    for (int c = 0; c < C; ++c) {
+      float v = logf(prob[c] + eps) + gum[c];
+      if (v > best || c == 0) { best = v; best_c = c; }  // first maximum wins (torch.max)
+    }
+    s_best[n] = best;
+    s_new[n] = best_c;
+  }
+  __syncthreads();
+
+  int64_t* out_row = a_out + smp * n_atoms;
+  if (one_transition) {
+    // generators/langevin_generator.py:339-380: only the most likely proposed change happens.
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int n = threadIdx.x; n < n_atoms; n += blockDim.x) {
+      float v = (s_new[n] != (int)a_row[n]) ? s_best[n] : -CUDART_INF_F;
+      if (v > bv || (v == bv && n < bi)) { bv = v; bi = n; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_down_sync(0xffffffffu, bv, o);
+      int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_red_val[warp] = bv; s_red_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = (blockDim.x + 31) >> 5;
+      bv = lane < nw ? s_red_val[lane] : -CUDART_INF_F;
+      bi = lane < nw ? s_red_idx[lane] : 0x7fffffff;
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_down_sync(0xffffffffu, bv, o);
+        int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) s_red_idx[0] = bi;
+    }
+    __syncthreads();
+    const int winner = s_red_idx[0];  // argmax of an all -inf row is atom 0, whose type is unchanged
+    for (int n = threadIdx.x; n < n_atoms; n += blockDim.x) {
+      int v = (n == winner) ? s_new[n] : (int)a_row[n];
+      out_row[n] = v;
+      if (last_step && v == mask_class) local_status |= B200MD_STATUS_MASK_REMAINS;
+    }
+  } else {
+    for (int n = threadIdx.x; n < n_atoms; n += blockDim.x) {
+      int v = s_new[n];
+      out_row[n] = v;
+      if (last_step && v == mask_class) local_status |= B200MD_STATUS_MASK_REMAINS;
+    }
+  }
+  if (local_status && status != nullptr) atomicOr(status, (int)local_status);
+}
+
+// -------------------------------------------------------------------------------------------------
+// RePaint overwrite.  One thread per (sample, constrained atom).
+//   generators/constrained_langevin_generator.py:74-82,120-163; data/diffusion/noising_transform.py:153-181;
+//   noisers/relative_coordinates_noiser.py:58-67; noisers/atom_types_noiser.py:50-60
+// -------------------------------------------------------------------------------------------------
+__global__ void repaint_kernel(float* __restrict__ x, int64_t* __restrict__ a, const float* __restrict__ x0,
+                               const int64_t* __restrict__ a0, const int64_t* __restrict__ idx,
+                               int32_t nc, float sigma_i, const float* __restrict__ qbar,
+                               const float* __restrict__ z, const float* __restrict__ u,
+                               int64_t n_samples, int32_t n_atoms, int32_t D, int32_t C, uint64_t seed,
+                               uint32_t step_id, uint64_t sample_offset) {
+  const int64_t total = n_samples * nc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t smp = t / nc;
+    const int32_t k = (int32_t)(t - smp * nc);
+    const int64_t atom = idx ? idx[k] : k;
+    const int64_t node = smp * n_atoms + atom;
+    const int a_known = (int)a0[k];
+    if (sigma_i < 0.f) {  // hard constraint (_apply_constraint)
+      for (int d = 0; d < D; ++d) x[node * D + d] = x0[k * D + d];
+      a[node] = a_known;
+      continue;
+    }
+    float zz[4];
+    if (z != nullptr) {
+      for (int d = 0; d < D; ++d) zz[d] = z[t * D + d];
+    } else {
+      Philox4 p = draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)k, step_id,
+                             B200MD_DRAW_REPAINT_NORMAL);
+      normal4(p, zz);
+    }
+    for (int d = 0; d < D; ++d)
+      x[node * D + d] = wrap_unit(__fadd_rn(x0[k * D + d], __fmul_rn(sigma_i, zz[d])));
+    // a_t = argmax_c log(Qbar[a0][c]) - log(-log(u_c))
+    float best = -CUDART_INF_F;
+    int best_c = 0;
+    const int nblk = (C + 3) >> 2;
+    for (int b = 0; b < nblk; ++b) {
+      float uu[4];
+      if (u != nullptr) {
+        for (int i = 0; i < 4 && b * 4 + i < C; ++i) uu[i] = u[t * C + b * 4 + i];
+      } else {
+        Philox4 p = draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)(k * nblk + b), step_id,
+                               B200MD_DRAW_REPAINT_UNIFORM);
+        uu[0] = u01(p.x); uu[1] = u01(p.y); uu[2] = u01(p.z); uu[3] = u01(p.w);
+      }
+      for (int i = 0; i < 4 && b * 4 + i < C; ++i) {
+        int c = b * 4 + i;
+        float v = logf(qbar[a_known * C + c]) + (-logf(-logf(uu[i])));
+        if (c == 0 || v > best) { best = v; best_c = c; }
+      }
+    }
+    a[node] = best_c;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Wrapped-Gaussian sigma-normalised score.   score/wrapped_gaussian_score.py:131-198,255-419
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void wrapped_gaussian_score_kernel(const T* __restrict__ u_in, const T* __restrict__ s_in,
+                                              int64_t n, int32_t kmax, T* __restrict__ out) {
+  const T pi = (T)3.14159265358979323846;
+  // SIGMA_THRESHOLD = torch.Tensor([1/sqrt(2 pi)]) is a float32 tensor (:37); comparing an f64 sigma with
+  // it promotes the float32 value, so the threshold is the float32-rounded number in both precisions.
+  const T sigma_threshold = (T)(float)0.3989422804014327;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const T u = u_in[i];
+    const T sigma = s_in[i];
+    T result;
+    if (sigma <= sigma_threshold) {
+      // small sigma: sigma*S = (-u - sum_k k e_k / sum_k e_k) / sigma            (:301-367)
+      const bool small_u = u < (T)0.5;
+      const T s2 = sigma * sigma;
+      T num = 0, den = 0;
+      for (int k = -kmax; k <= kmax; ++k) {
+        const T kk = (T)k;
+        T arg;
+        if (small_u) arg = (T)(-0.5) * (kk * kk + (T)2.0 * u * kk) / s2;                       // (:271-273)
+        else arg = (T)(-0.5) * ((kk * kk - (T)1.0) + (T)2.0 * u * (kk + (T)1.0)) / s2;         // (:294-297)
+        const T e = exp(arg);
+        num += kk * e;
+        den += e;
+      }
+      result = (-u - num / den) / sigma;
+    } else {
+      // large sigma, Ewald form (:369-419)
+      T z2a = 0, z2b = 0, d1 = 0, d2 = 0;
+      for (int k = -kmax; k <= kmax; ++k) {
+        const T g = (T)k;
+        const T upk = u + g;
+        const T gu = u * g;
+        const T sg = sigma * g;
+        const T exp_upk = exp(-pi * upk * upk);
+        const T exp_sg = exp((T)(-2.0) * pi * pi * sg * sg);
+        const T exp_g = exp(-pi * g * g);
+        const T comb = sqrt((T)2.0 * pi) * sigma * exp_sg - exp_g;
+        T sn, cs;
+        sincos((T)2.0 * pi * gu, &sn, &cs);
+        z2a += exp_upk;
+        z2b += comb * cs;
+        d1 += upk * exp_upk;
+        d2 += g * comb * sn;
+      }
+      const T z2 = z2a + z2b;
+      const T deriv = (T)(-2.0) * pi * (d1 + d2);
+      result = sigma * deriv / z2;
+    }
+    out[i] = result;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// unsorted_segment_sum / mean   models/egnn_utils.py:11-70   (atomic scatter-add; ids need not be sorted)
+// -------------------------------------------------------------------------------------------------
+__global__ void segment_scatter_kernel(const float* __restrict__ data, const int64_t* __restrict__ ids,
+                                       int64_t n_elements, int32_t F, float* __restrict__ out,
+                                       float* __restrict__ counts) {
+  const int64_t total = n_elements * F;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = t / F;
+    const int32_t f = (int32_t)(t - e * F);
+    const int64_t seg = ids[e];
+    atomicAdd(out + seg * F + f, data[t]);
+    if (counts != nullptr && f == 0) atomicAdd(counts + seg, 1.0f);
+  }
+}
+__global__ void segment_mean_finish_kernel(float* __restrict__ out, const float* __restrict__ counts,
+                                           int64_t num_segments, int32_t F) {
+  const int64_t total = num_segments * F;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = out[t] / fmaxf(counts[t / F], 1.0f);
+}
+
+static inline unsigned grid_for(int64_t total, int threads) {
+  int64_t b = ceil_div64(total, threads);
+  if (b > 148 * 32) b = 148 * 32;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace b200md
+
+using namespace b200md;
+
+extern "C" {
+
+int b200md_draw_normal(float* out, int64_t n_samples, int32_t units, int32_t unit_size, uint64_t seed,
+                       uint32_t step_id, uint32_t draw_id, uint64_t sample_offset,
+                       b200md_stream_t stream) {
+  return launch_draw<kNormal>(out, n_samples, units, unit_size, 0.f, seed, step_id, draw_id,
+                              sample_offset, stream);
+}
+int b200md_draw_uniform(float* out, int64_t n_samples, int32_t units, int32_t unit_size, uint64_t seed,
+                        uint32_t step_id, uint32_t draw_id, uint64_t sample_offset,
+                        b200md_stream_t stream) {
+  return launch_draw<kUniform>(out, n_samples, units, unit_size, 0.f, seed, step_id, draw_id,
+                               sample_offset, stream);
+}
+int b200md_draw_gumbel(float* out, int64_t n_samples, int32_t units, int32_t unit_size,
+                       float small_epsilon, uint64_t seed, uint32_t step_id, uint32_t draw_id,
+                       uint64_t sample_offset, b200md_stream_t stream) {
+  return launch_draw<kGumbel>(out, n_samples, units, unit_size, small_epsilon, seed, step_id, draw_id,
+                              sample_offset, stream);
+}
+
+int b200md_wrap_to_unit_cell(const float* x, float* out, int64_t n, b200md_stream_t stream) {
+  if (n < 0 || (n > 0 && (!x || !out))) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n == 0) return B200MD_OK;
+  wrap_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_pc_coordinates_update(const float* x, const float* s, const float* z, float score_weight,
+                                 float sigma, float noise_weight, int64_t n_samples, int32_t n_atoms,
+                                 int32_t D, uint64_t seed, uint32_t step_id, uint64_t sample_offset,
+                                 float* x_out, b200md_stream_t stream) {
+  if (!x || !s || !x_out || n_samples < 0 || n_atoms <= 0 || D < 1 || D > 3)
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0) return B200MD_OK;
+  const int64_t total = n_samples * n_atoms;
+  const unsigned g = grid_for(total, 256);
+  cudaStream_t st = as_stream(stream);
+  switch (D) {
+    case 1: pc_coordinates_update_kernel<1><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+    case 2: pc_coordinates_update_kernel<2><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+    default: pc_coordinates_update_kernel<3><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+  }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_pc_lattice_update(const float* l, const float* s, const float* z, float score_weight,
+                             float sigma_n, float noise_weight, int64_t n_samples, int32_t n_lp,
+                             uint64_t seed, uint32_t step_id, uint64_t sample_offset, float* l_out,
+                             b200md_stream_t stream) {
+  if (!l || !s || !l_out || n_samples < 0 || n_lp <= 0) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0) return B200MD_OK;
+  const int64_t total = n_samples * ((n_lp + 2) / 3);
+  pc_lattice_update_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
+      l, s, z, score_weight, sigma_n, noise_weight, n_samples, n_lp, seed, step_id, sample_offset, l_out);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_atom_types_update(const float* logits, const int64_t* atom_types, const float* q,
+                             const float* q_bar, const float* q_bar_tm1, const float* gumbel,
+                             const float* binary, int32_t flags, float small_epsilon,
+                             int64_t n_samples, int32_t n_atoms, int32_t n_classes, uint64_t seed,
+                             uint32_t step_id, uint64_t sample_offset, int64_t* atom_types_out,
+                             float* probs_out, int32_t* status, b200md_stream_t stream) {
+  if (!logits || !atom_types || !q || !q_bar || !q_bar_tm1 || !atom_types_out || n_samples < 0 ||
+      n_atoms <= 0 || n_classes < 2)
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_classes > kMaxClasses) return B200MD_ERR_UNSUPPORTED;
+  if (n_samples == 0) return B200MD_OK;
+  int threads = ((n_atoms + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  size_t smem = (size_t)3 * n_classes * n_classes * sizeof(float) + (size_t)n_atoms * 8;
+  if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(atom_types_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  atom_types_update_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+      logits, atom_types, q, q_bar, q_bar_tm1, gumbel, binary, flags, small_epsilon, n_atoms, n_classes,
+      seed, step_id, sample_offset, atom_types_out, probs_out, status);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_repaint(float* x, int64_t* atom_types, const float* x0_known, const int64_t* a0_known,
+                   const int64_t* constrained_indices, int32_t n_constrained, float sigma_i,
+                   const float* q_bar_i, const float* z, const float* u, int64_t n_samples,
+                   int32_t n_atoms, int32_t D, int32_t n_classes, uint64_t seed, uint32_t step_id,
+                   uint64_t sample_offset, b200md_stream_t stream) {
+  if (!x || !atom_types || !x0_known || !a0_known || n_constrained < 0 || n_samples < 0 || D < 1 ||
+      D > 3 || (sigma_i >= 0.f && !q_bar_i))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0 || n_constrained == 0) return B200MD_OK;
+  const int64_t total = n_samples * n_constrained;
+  repaint_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
+      x, atom_types, x0_known, a0_known, constrained_indices, n_constrained, sigma_i, q_bar_i, z, u,
+      n_samples, n_atoms, D, n_classes, seed, step_id, sample_offset);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_wrapped_gaussian_score_f32(const float* u, const float* sigma, int64_t n, int32_t kmax,
+                                      float* out, b200md_stream_t stream) {
+  if (n < 0 || kmax < 0 || (n > 0 && (!u || !sigma || !out))) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n == 0) return B200MD_OK;
+  wrapped_gaussian_score_kernel<float><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+int b200md_wrapped_gaussian_score_f64(const double* u, const double* sigma, int64_t n, int32_t kmax,
+                                      double* out, b200md_stream_t stream) {
+  if (n < 0 || kmax < 0 || (n > 0 && (!u || !sigma || !out))) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n == 0) return B200MD_OK;
+  wrapped_gaussian_score_kernel<double><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out);
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_segment_reduce(const float* data, const int64_t* segment_ids, int64_t n_elements,
+                          int32_t n_features, int64_t num_segments, int32_t mean, float* out,
+                          float* scratch_counts, b200md_stream_t stream) {
+  if (n_elements < 0 || n_features <= 0 || num_segments < 0 || !out || (mean && !scratch_counts))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  if (num_segments == 0) return B200MD_OK;
+  cudaMemsetAsync(out, 0, sizeof(float) * num_segments * n_features, st);
+  if (mean) cudaMemsetAsync(scratch_counts, 0, sizeof(float) * num_segments, st);
+  if (n_elements > 0) {
+    if (!data || !segment_ids) return B200MD_ERR_INVALID_ARGUMENT;
+    segment_scatter_kernel<<<grid_for(n_elements * n_features, 256), 256, 0, st>>>(
+        data, segment_ids, n_elements, n_features, out, mean ? scratch_counts : nullptr);
+    B200MD_CHECK_LAUNCH();
+  }
+  if (mean) {
+    segment_mean_finish_kernel<<<grid_for(num_segments * n_features, 256), 256, 0, st>>>(
+        out, scratch_counts, num_segments, n_features);
+    B200MD_CHECK_LAUNCH();
+  }
+  return B200MD_OK;
+}
+
+}  // extern "C"

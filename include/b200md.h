@@ -1,0 +1,319 @@
+/*
+ * b200md.h -- C ABI of the B200-native predictor-corrector sampling hot path.
+ *
+ * This is the drop-in boundary for ONE path of mila-iqia/diffusion_for_multi_scale_molecular_dynamics:
+ * LangevinGenerator (PC sampler) -> EGNNScoreNetwork -> periodic radius graph / EGNN message passing /
+ * wrapped-Gaussian score / fused predictor-corrector update.  The reference has no FFI layer of its own
+ * (it is pure Python/PyTorch); every entry point below therefore cites the reference *Python* interface
+ * it replaces (paths relative to src/diffusion_for_multi_scale_molecular_dynamics/ in the reference).
+ *
+ * Conventions
+ *  - plain C, no torch types; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - memory is owned by the caller (PyTorch); the library never allocates device memory;
+ *  - every launch goes on the `stream` argument (a cudaStream_t passed as void*);
+ *  - return value: 0 on success, negative b200md_error on failure (see b200md_error_string);
+ *  - data-dependent failures (the reference's `assert tensor.all()` host syncs) are reported through a
+ *    device-side int32 `status` word (bitwise OR of B200MD_STATUS_*) that the host wrapper reads once per
+ *    sample() instead of once per step;
+ *  - floating point is fp32, atom types / edge indices at the boundary are int64 (as in the reference).
+ */
+#ifndef B200MD_H_
+#define B200MD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MD_ABI_VERSION 1
+
+typedef void* b200md_stream_t; /* cudaStream_t */
+
+typedef enum {
+  B200MD_OK = 0,
+  B200MD_ERR_INVALID_ARGUMENT = -1,
+  B200MD_ERR_CUDA = -2,
+  B200MD_ERR_UNSUPPORTED = -3,
+  B200MD_ERR_WORKSPACE_TOO_SMALL = -4
+} b200md_error;
+
+/* bits of the device-side status word */
+#define B200MD_STATUS_X_OUT_OF_RANGE 1u     /* models/score_networks/score_network.py:110-114 */
+#define B200MD_STATUS_A_OUT_OF_RANGE 2u     /* models/score_networks/score_network.py:159-165 */
+#define B200MD_STATUS_CUTOFF_TOO_LARGE 4u   /* utils/neighbors.py:107-113 */
+#define B200MD_STATUS_EDGE_OVERFLOW 8u      /* edge workspace capacity exceeded (no reference analogue) */
+#define B200MD_STATUS_MASK_REMAINS 16u      /* generators/langevin_generator.py:616-620 */
+#define B200MD_STATUS_BAD_LOGITS 32u        /* utils/d3pm_utils.py:143-145 */
+#define B200MD_STATUS_SIGMA_OUT_OF_RANGE 64u
+
+const char* b200md_error_string(int code);
+int b200md_abi_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t b200md_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Counter-based noise (replaces the CPU torch.rand/randn + H2D copy of
+ * generators/langevin_generator.py:92-111 and generators/trajectory_initializer.py:109-119).
+ * Value (sample s, unit u, lane l) depends only on (seed, s + sample_offset, u, l, step_id, draw_id):
+ * results are independent of batch chunking and of the number of GPUs.
+ * `unit_size` = values per unit (3 for coordinates, num_classes for Gumbel, 1 for the greedy binary draw).
+ * ---------------------------------------------------------------------------------------------- */
+#define B200MD_DRAW_COORD_NORMAL 0u
+#define B200MD_DRAW_GUMBEL 1u
+#define B200MD_DRAW_BINARY 2u
+#define B200MD_DRAW_LATTICE_NORMAL 3u
+#define B200MD_DRAW_INIT_UNIFORM 4u
+#define B200MD_DRAW_REPAINT_NORMAL 5u
+#define B200MD_DRAW_REPAINT_UNIFORM 6u
+#define B200MD_DRAW_REPAINT_INIT 7u
+
+int b200md_draw_normal(float* out, int64_t n_samples, int32_t units_per_sample, int32_t unit_size,
+                       uint64_t seed, uint32_t step_id, uint32_t draw_id, uint64_t sample_offset,
+                       b200md_stream_t stream);
+int b200md_draw_uniform(float* out, int64_t n_samples, int32_t units_per_sample, int32_t unit_size,
+                        uint64_t seed, uint32_t step_id, uint32_t draw_id, uint64_t sample_offset,
+                        b200md_stream_t stream);
+/* -log(-log(clip(u, small_epsilon)))  (langevin_generator.py:100-107) */
+int b200md_draw_gumbel(float* out, int64_t n_samples, int32_t units_per_sample, int32_t unit_size,
+                       float small_epsilon, uint64_t seed, uint32_t step_id, uint32_t draw_id,
+                       uint64_t sample_offset, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * map_relative_coordinates_to_unit_cell (utils/basis_transformations.py:95-119):
+ * out = remainder(x, 1); out[out == 1] = 0.   `out` may alias `x`.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_wrap_to_unit_cell(const float* x, float* out, int64_t n, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LangevinGenerator._relative_coordinates_update (generators/langevin_generator.py:155-201), used by both
+ * predictor_step (:623-629) and corrector_step (:740-758):
+ *   x_out = wrap( (x + (score_weight * s) / sigma) + noise_weight * z )
+ * z is read from `z_or_null` when given, otherwise drawn in-kernel
+ * (draw_id B200MD_DRAW_COORD_NORMAL, unit = atom).  `x_out` may alias `x`.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_pc_coordinates_update(const float* x, const float* sigma_normalized_score,
+                                 const float* z_or_null, float score_weight, float sigma,
+                                 float noise_weight, int64_t n_samples, int32_t n_atoms,
+                                 int32_t spatial_dimension, uint64_t seed, uint32_t step_id,
+                                 uint64_t sample_offset, float* x_out, b200md_stream_t stream);
+
+/* LangevinGenerator._lattice_parameters_update (langevin_generator.py:441-490):
+ *   l_out = (l + (score_weight * s) / sigma_n) + noise_weight * z          (no wrap)            */
+int b200md_pc_lattice_update(const float* l, const float* sigma_normalized_score,
+                             const float* z_or_null, float score_weight, float sigma_n,
+                             float noise_weight, int64_t n_samples, int32_t n_lattice_parameters,
+                             uint64_t seed, uint32_t step_id, uint64_t sample_offset, float* l_out,
+                             b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LangevinGenerator._atom_types_update (langevin_generator.py:247-439) fused with
+ * get_probability_at_previous_time_step / get_probability_from_logits (utils/d3pm_utils.py:64-150).
+ * q / q_bar / q_bar_tm1 are the [C,C] matrices of the current time index (device pointers into the
+ * NoiseScheduler tables).  gumbel [B,N,C] and binary [B,N] are injected when non-NULL, else drawn.
+ * flags: bit0 greedy sampling, bit1 one transition per step, bit2 last time step (assert no MASK -> status).
+ * Optional outputs (may be NULL): probs_out [B,N,C] = p(a_{t-1}|a_t) after the greedy adjustment.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200MD_ATOM_GREEDY 1
+#define B200MD_ATOM_ONE_TRANSITION 2
+#define B200MD_ATOM_LAST_STEP 4
+int b200md_atom_types_update(const float* logits, const int64_t* atom_types, const float* q,
+                             const float* q_bar, const float* q_bar_tm1,
+                             const float* gumbel_or_null, const float* binary_or_null,
+                             int32_t flags, float small_epsilon, int64_t n_samples,
+                             int32_t n_atoms, int32_t n_classes, uint64_t seed, uint32_t step_id,
+                             uint64_t sample_offset, int64_t* atom_types_out, float* probs_out,
+                             int32_t* status, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RePaint overwrite (generators/constrained_langevin_generator.py:74-82,120-163 with
+ * data/diffusion/noising_transform.py:98-200, noisers/relative_coordinates_noiser.py:33-67,
+ * noisers/atom_types_noiser.py:30-60):
+ *   X[:, idx] = wrap(x0_known + sigma_i * z)          (sigma_i < 0  => hard constraint, no noise)
+ *   A[:, idx] = argmax(log(onehot(a0_known) Qbar_i) + gumbel(u))
+ * In place on X [B,N,d] and A [B,N].  z [B,Nc,d] / u [B,Nc,C] injected when non-NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_repaint(float* x, int64_t* atom_types, const float* x0_known, const int64_t* a0_known,
+                   const int64_t* constrained_indices, int32_t n_constrained, float sigma_i,
+                   const float* q_bar_i, const float* z_or_null, const float* u_or_null,
+                   int64_t n_samples, int32_t n_atoms, int32_t spatial_dimension,
+                   int32_t n_classes, uint64_t seed, uint32_t step_id, uint64_t sample_offset,
+                   b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * get_coordinates_sigma_normalized_score (score/wrapped_gaussian_score.py:131-198): sigma-normalised score
+ * of the wrapped Gaussian, lattice-image sum k in [-kmax, kmax], three numerically stable branches
+ * (:201-419).  u in [0,1), sigma > 0, both [n].  f32 and f64 variants.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_wrapped_gaussian_score_f32(const float* u, const float* sigma, int64_t n, int32_t kmax,
+                                      float* out, b200md_stream_t stream);
+int b200md_wrapped_gaussian_score_f64(const double* u, const double* sigma, int64_t n,
+                                      int32_t kmax, double* out, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * unsorted_segment_sum / unsorted_segment_mean (models/egnn_utils.py:11-70).
+ * data [E,F] f32, segment_ids [E] int64 in [0,num_segments); out [num_segments,F].
+ * `scratch_counts` [num_segments] f32 is needed for mean.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_segment_reduce(const float* data, const int64_t* segment_ids, int64_t n_elements,
+                          int32_t n_features, int64_t num_segments, int32_t mean, float* out,
+                          float* scratch_counts, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Periodic radius graph.
+ *
+ * b200md_radius_graph_count / _fill replace get_periodic_adjacency_information
+ * (utils/neighbors.py:36-224), get_adj_matrix (models/graph_utils.py:10-50) and
+ * get_edges_with_radial_cutoff (models/egnn_utils.py:107-144).
+ *
+ * positions [B,N,3]: Cartesian (positions_are_relative = 0) or relative coordinates (1; p = x @ cell is
+ * then formed in-kernel, basis_transformations.py:56).  cell [B,3,3], rows are a1,a2,a3.
+ * Edge test, in fp32 without FMA contraction (dense semantics of neighbors.py:170,188-190):
+ *     shifted = p_j + (n @ cell);  diff = p_i - shifted;  d2 = (dx*dx + dy*dy) + dz*dz;  0 < d2 <= rc*rc
+ * over the 27 images n in {-1,0,1}^3 in itertools.product order (utils/lattice_utils.py:24-27).
+ *
+ * mode B200MD_GRAPH_UNIQUE_PAIRS : one edge per ordered pair (src,dst) having >= 1 image inside the cutoff,
+ *      sorted by (batch, src, dst) -- the torch.unique(dim=1) form of egnn_utils.py:139-142.
+ *      counts are per (b, src): counts [B*N].
+ * mode B200MD_GRAPH_PER_IMAGE : one edge per (image, src, dst), order (batch, image, src, ascending d2,
+ *      ties by dst) -- the native AdjacencyInfo order.  counts [B*27*N].
+ *
+ * count: writes `counts` (int32) and per-structure totals `edges_per_structure` [B] (int64) and sets
+ *        B200MD_STATUS_CUTOFF_TOO_LARGE when rc >= the shortest cell-crossing distance
+ *        (neighbors.py:248-351).
+ * fill : given `offsets` = exclusive scan of `counts` (int64, length = len(counts)), writes
+ *        src/dst int64 (local atom indices + node_index_offset*b, so node_index_offset = N gives the
+ *        graph-batched indices of neighbors.py:381-390), optional shifts [E,3] f32 (the lattice vector
+ *        n @ cell of each edge) and optional edge_batch_indices [E] int64.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200MD_GRAPH_UNIQUE_PAIRS 0
+#define B200MD_GRAPH_PER_IMAGE 1
+int b200md_radius_graph_count(const float* positions, const float* cell,
+                              int32_t positions_are_relative, float radial_cutoff, int64_t n_samples,
+                              int32_t n_atoms, int32_t mode, int32_t* counts,
+                              int64_t* edges_per_structure, int32_t* status,
+                              b200md_stream_t stream);
+int b200md_radius_graph_fill(const float* positions, const float* cell,
+                             int32_t positions_are_relative, float radial_cutoff, int64_t n_samples,
+                             int32_t n_atoms, int32_t mode, const int64_t* offsets,
+                             int64_t node_index_offset, int64_t* src_out, int64_t* dst_out,
+                             float* shifts_out_or_null, int64_t* edge_batch_or_null,
+                             b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * EGNN score network: EGNNScoreNetwork._forward_unchecked (models/score_networks/egnn_score_network.py:226-303)
+ * + EGNN / E_GCL (models/egnn.py:266-288,362-385) + the MASK-logit rule of ScoreNetwork.forward
+ * (models/score_networks/score_network.py:183-185,221).
+ * ---------------------------------------------------------------------------------------------- */
+#define B200MD_EGNN_RESIDUAL 1
+#define B200MD_EGNN_ATTENTION 2
+#define B200MD_EGNN_NORMALIZE 4
+#define B200MD_EGNN_TANH 8
+#define B200MD_EGNN_COORDS_MEAN 16
+#define B200MD_EGNN_MESSAGE_MEAN 32
+#define B200MD_EGNN_RADIAL_CUTOFF 64   /* edges="radial_cutoff" (else fully connected) */
+#define B200MD_EGNN_KEEP_DUPLICATES 128 /* drop_duplicate_edges=False */
+
+typedef struct {
+  int32_t spatial_dimension;      /* 3 */
+  int32_t num_atom_types;         /* excluding MASK */
+  int32_t n_layers;
+  int32_t n_bloch;                /* number of Bloch wave vectors; uplift dimension is 2*n_bloch */
+  int32_t node_hidden;            /* node_hidden_dimensions_size  (H) */
+  int32_t node_n_hidden;          /* node_n_hidden_dimensions */
+  int32_t message_hidden;         /* message_hidden_dimensions_size (M) */
+  int32_t message_n_hidden;
+  int32_t coord_hidden;           /* coordinate_hidden_dimensions_size (Cx) */
+  int32_t coord_n_hidden;
+  int32_t flags;                  /* B200MD_EGNN_* */
+  float radial_cutoff;            /* Angstrom; used when B200MD_EGNN_RADIAL_CUTOFF */
+  float lattice_clip_min;         /* float32(2.2 * radial_cutoff), egnn_score_network.py:236-239 */
+} b200md_egnn_config;
+
+/* Parameters are handed over in state_dict order of the reference module (egnn_score_network.py /
+ * egnn.py; names in SURVEY.md section 8 a-12):
+ *   bloch_wave_reciprocal_lattice_vectors [n_bloch,3], projection_matrices [3,2n,2n],
+ *   egnn.embedding_in.{weight,bias},
+ *   per layer: message_mlp.{0,2,..}.{weight,bias}, node_mlp.{0,2,..,last}.{weight,bias},
+ *              coord_mlp.{0,2,..}.{weight,bias}, coord_mlp.last.weight, [att_mlp.0.{weight,bias}],
+ *   egnn.node_classification_layer.{weight,bias}.
+ * b200md_egnn_param_count gives the expected number of tensors, b200md_egnn_packed_floats the size of the
+ * packed image (fp32 words) the caller must allocate; b200md_egnn_pack_weights fills it (device->device).
+ * `param_ptrs_host` is a HOST array of DEVICE pointers.                                            */
+int32_t b200md_egnn_param_count(const b200md_egnn_config* cfg);
+int64_t b200md_egnn_packed_floats(const b200md_egnn_config* cfg);
+int b200md_egnn_pack_weights(const b200md_egnn_config* cfg, const float* const* param_ptrs_host,
+                             int32_t n_params, float* packed, b200md_stream_t stream);
+
+/* Workspace (bytes) for a forward over B structures of N atoms with room for `edge_capacity` directed
+ * edges in total.  b200md_egnn_default_edge_capacity gives a safe default (all pairs when N is small).   */
+int64_t b200md_egnn_default_edge_capacity(const b200md_egnn_config* cfg, int64_t n_samples,
+                                          int32_t n_atoms, const float* cell_lengths_host_or_null);
+int64_t b200md_egnn_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_samples,
+                                    int32_t n_atoms, int64_t edge_capacity);
+
+#define B200MD_IMPL_AUTO 0
+#define B200MD_IMPL_FFMA 1    /* fp32 CUDA-core tiles */
+#define B200MD_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma tiles, fp32 accumulate in TMEM */
+
+/* atom_types [B,N] int64, x [B,N,3] in [0,1), lattice [B,6], sigma [B] ->
+ * logits_out [B,N,C] (C = num_atom_types+1; MASK logit = -inf when mask_logit_to_neg_inf),
+ * score_out [B,N,3] (sigma-normalised score).  The lattice output of the reference is identically zero
+ * (egnn_score_network.py:296-300) and is produced by the host wrapper.
+ * Optional debug output: n_edges_out (device int64[1]) total number of edges of the graph used.        */
+int b200md_egnn_forward(const b200md_egnn_config* cfg, const float* packed,
+                        const int64_t* atom_types, const float* x, const float* lattice,
+                        const float* sigma, int64_t n_samples, int32_t n_atoms,
+                        int32_t mask_logit_to_neg_inf, float* logits_out, float* score_out,
+                        void* workspace, int64_t workspace_bytes, int64_t edge_capacity,
+                        int64_t* n_edges_out_or_null, int32_t* status, int32_t impl,
+                        b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole predictor-corrector trajectory: PredictorCorrectorAXLGenerator.sample_from_noisy_composition
+ * (generators/predictor_corrector_axl_generator.py:112-161) driving LangevinGenerator.predictor_step /
+ * corrector_step (generators/langevin_generator.py:536-645,693-805) with the EGNN score network, every
+ * launch enqueued from one host call, noise drawn in-kernel, no host synchronisation.
+ * Schedule tables are DEVICE arrays from NoiseScheduler (noise_schedulers/noise_scheduler.py:348-378):
+ * sigma,g,g2 [T]; epsilon [T]; q,q_bar,q_bar_tm1 [T,C,C]; the host copies `*_host` [T] drive kernel arguments.
+ * In place on atom_types [B,N], x [B,N,3]; lattice [B,6] is fixed (use_fixed_lattice_parameters=True).
+ * Optional constraint (RePaint, constrained_langevin_generator.py) when n_constrained > 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t total_time_steps;           /* T */
+  int32_t number_of_corrector_steps;
+  int32_t start_step_index;           /* starting_step_index (T for a full trajectory) */
+  int32_t end_step_index;             /* ending_step_index (0) */
+  int32_t atom_flags;                 /* B200MD_ATOM_GREEDY | B200MD_ATOM_ONE_TRANSITION */
+  int32_t atom_type_transition_in_corrector;
+  float small_epsilon;
+  float sigma_min;                    /* corrector at i == 0 (langevin_generator.py:719-725) */
+  const float* sigma_host;            /* [T] */
+  const float* g_host;                /* [T] */
+  const float* g2_host;               /* [T] */
+  const float* epsilon_host;          /* [T] */
+  const float* sqrt_2_epsilon_host;   /* [T] */
+  const float* q;                     /* device [T,C,C] */
+  const float* q_bar;                 /* device [T,C,C] */
+  const float* q_bar_tm1;             /* device [T,C,C] */
+  /* RePaint */
+  int32_t n_constrained;
+  const float* x0_known;              /* device [Nc,3] */
+  const int64_t* a0_known;            /* device [Nc] */
+  const int64_t* constrained_indices; /* device [Nc] */
+} b200md_pc_schedule;
+
+int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed,
+                     const b200md_pc_schedule* schedule, int64_t* atom_types, float* x,
+                     const float* lattice, int64_t n_samples, int32_t n_atoms, uint64_t seed,
+                     uint64_t sample_offset, void* workspace, int64_t workspace_bytes,
+                     int64_t edge_capacity, int32_t* status, int32_t impl, b200md_stream_t stream);
+/* extra workspace b200md_pc_sample needs on top of b200md_egnn_workspace_bytes */
+int64_t b200md_pc_sample_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_samples,
+                                         int32_t n_atoms, int64_t edge_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MD_H_ */
