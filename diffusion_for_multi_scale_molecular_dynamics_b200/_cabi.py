@@ -107,6 +107,8 @@ SIGNATURES = {
     "b200md_error_string": (c_char_p, [c_int32]),
     "b200md_abi_version": (c_int32, []),
     "b200md_launch_count": (c_uint64, []),
+    "b200md_profile_enable": (c_int32, [c_int32]),
+    "b200md_profile_collect": (c_int32, [POINTER(ctypes.c_double), POINTER(c_int64), c_int32]),
     "b200md_draw_normal": (c_int32, [_P, c_int64, c_int32, c_int32, c_uint64, c_uint32, c_uint32, c_uint64, _P]),
     "b200md_draw_uniform": (c_int32, [_P, c_int64, c_int32, c_int32, c_uint64, c_uint32, c_uint32, c_uint64, _P]),
     "b200md_draw_gumbel": (c_int32, [_P, c_int64, c_int32, c_int32, c_float, c_uint64, c_uint32, c_uint32, c_uint64, _P]),
@@ -140,6 +142,7 @@ SIGNATURES = {
     "b200md_egnn_pack_weights": (c_int32, [_CFG, POINTER(c_void_p), c_int32, _P, _P]),
     "b200md_egnn_default_edge_capacity": (c_int64, [_CFG, c_int64, c_int32, POINTER(c_float)]),
     "b200md_egnn_workspace_bytes": (c_int64, [_CFG, c_int64, c_int32, c_int64]),
+    "b200md_egnn_resolve_impl": (c_int32, [_CFG, c_int32]),
     "b200md_egnn_forward": (
         c_int32,
         [_CFG, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, c_int64, _P, _P, c_int32, _P],
@@ -227,6 +230,22 @@ def raise_on_status(status: torch.Tensor, error=AssertionError) -> None:
         messages = [text for bit, text in STATUS_MESSAGES.items() if word & bit]
         status.zero_()
         raise error(" ".join(messages) if messages else f"device status {word}")
+
+
+KERNEL_CLASSES = ("graph", "node", "edge", "update", "other")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().b200md_profile_enable(int(on)))
+
+
+def profile_collect() -> dict:
+    """{class: (milliseconds, launches)} accumulated since the last collect (synchronises the recorded events)."""
+    n = len(KERNEL_CLASSES)
+    ms = (ctypes.c_double * n)()
+    launches = (c_int64 * n)()
+    check(lib().b200md_profile_collect(ms, launches, n))
+    return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(KERNEL_CLASSES)}
 
 
 def launch_count() -> int:

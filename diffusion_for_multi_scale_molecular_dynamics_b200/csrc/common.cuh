@@ -18,6 +18,19 @@ extern unsigned long long g_launch_count;  // host-side counter, see api.cu
 
 int set_cuda_error(cudaError_t e);
 
+// In-stream timing of one launch (see b200md_profile_enable): records an event pair around the scope when
+// profiling is on; costs one predictable branch when it is off.
+extern bool g_profile_on;
+void profile_begin(int kernel_class, cudaStream_t st, cudaEvent_t* e0);
+void profile_end(int kernel_class, cudaStream_t st, cudaEvent_t e0);
+struct ProfileScope {
+  int cls; cudaStream_t st; cudaEvent_t e0; bool on;
+  ProfileScope(int kernel_class, cudaStream_t stream) : cls(kernel_class), st(stream), e0(nullptr), on(g_profile_on) {
+    if (on) profile_begin(cls, st, &e0);
+  }
+  ~ProfileScope() { if (on) profile_end(cls, st, e0); }
+};
+
 static inline cudaStream_t as_stream(b200md_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -103,12 +103,12 @@ __global__ void pack_copy_kernel(const float* __restrict__ src, int n, int strid
 }
 
 static int pack_t(const float* src, int n_out, int ld, int k0, int K, float* dst, cudaStream_t st) {
-  pack_transpose_kernel<<<64, 256, 0, st>>>(src, n_out, ld, k0, K, dst);
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, st); pack_transpose_kernel<<<64, 256, 0, st>>>(src, n_out, ld, k0, K, dst); }
   B200MD_CHECK_LAUNCH();
   return 0;
 }
 static int pack_c(const float* src, int n, int stride, float* dst, cudaStream_t st) {
-  pack_copy_kernel<<<8, 256, 0, st>>>(src, n, stride, dst);
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, st); pack_copy_kernel<<<8, 256, 0, st>>>(src, n, stride, dst); }
   B200MD_CHECK_LAUNCH();
   return 0;
 }
@@ -569,7 +569,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
   // call 0: embedding + uplift + partial products of layer 0
   na.do_embed = 1; na.do_update = 0; na.do_pq = 1; na.do_readout = 0;
   na.msg_wa_t = lay.layer[0].msg_wa_t; na.msg_wb_t = lay.layer[0].msg_wb_t; na.msg_b0 = lay.layer[0].msg_b0;
-  egnn_node_kernel<<<node_grid, kThreads, node_smem_bytes(), st>>>(na);
+  { ProfileScope ps__(B200MD_KERNEL_NODE, st); egnn_node_kernel<<<node_grid, kThreads, node_smem_bytes(), st>>>(na); }
   B200MD_CHECK_LAUNCH();
 
   for (int l = 0; l < cfg.n_layers; ++l) {
@@ -588,7 +588,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
       ea.off = lay.layer[l];
       int64_t max_tiles = ceil_div64(edge_capacity, kTE);
       unsigned grid = (unsigned)(max_tiles < 148 * 2 ? (max_tiles < 1 ? 1 : max_tiles) : 148 * 2);
-      egnn_edge_kernel<<<grid, kThreads, edge_smem_bytes(), st>>>(ea);
+      { ProfileScope ps__(B200MD_KERNEL_EDGE, st); egnn_edge_kernel<<<grid, kThreads, edge_smem_bytes(), st>>>(ea); }
       B200MD_CHECK_LAUNCH();
     }
     const bool last = (l == cfg.n_layers - 1);
@@ -599,7 +599,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
     if (!last) {
       na.msg_wa_t = lay.layer[l + 1].msg_wa_t; na.msg_wb_t = lay.layer[l + 1].msg_wb_t; na.msg_b0 = lay.layer[l + 1].msg_b0;
     }
-    egnn_node_kernel<<<node_grid, kThreads, node_smem_bytes(), st>>>(na);
+    { ProfileScope ps__(B200MD_KERNEL_NODE, st); egnn_node_kernel<<<node_grid, kThreads, node_smem_bytes(), st>>>(na); }
     B200MD_CHECK_LAUNCH();
   }
   return B200MD_OK;
@@ -709,6 +709,17 @@ int64_t b200md_egnn_workspace_bytes(const b200md_egnn_config* cfg, int64_t B, in
   if (!cfg || B < 0 || N <= 0 || cap < 0) return B200MD_ERR_INVALID_ARGUMENT;
   EgnnWorkspace ws;
   return carve_workspace(*cfg, B, N, cap, nullptr, ws);
+}
+
+int b200md_egnn_resolve_impl(const b200md_egnn_config* cfg, int32_t impl) {
+  if (!cfg) return B200MD_ERR_INVALID_ARGUMENT;
+  EgnnLayout lay;
+  int rc = build_layout(*cfg, lay);
+  if (rc != B200MD_OK) return rc;
+  if (impl == B200MD_IMPL_FFMA) return B200MD_IMPL_FFMA;
+  if (impl == B200MD_IMPL_TCGEN05) return tc_edge_supported(*cfg) ? B200MD_IMPL_TCGEN05 : B200MD_ERR_UNSUPPORTED;
+  if (impl == B200MD_IMPL_AUTO) return tc_edge_supported(*cfg) ? B200MD_IMPL_TCGEN05 : B200MD_IMPL_FFMA;
+  return B200MD_ERR_INVALID_ARGUMENT;
 }
 
 int b200md_egnn_forward(const b200md_egnn_config* cfg, const float* packed, const int64_t* atom_types,

@@ -52,8 +52,8 @@ static int launch_draw(float* out, int64_t n_samples, int32_t units, int32_t uni
   int threads = 256;
   int64_t blocks = ceil_div64(total, threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  draw_kernel<KIND><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
-      out, n_samples, units, unit_size, eps, seed, step_id, draw_id, sample_offset);
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); draw_kernel<KIND><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+      out, n_samples, units, unit_size, eps, seed, step_id, draw_id, sample_offset); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -61,7 +61,7 @@ static int launch_draw(float* out, int64_t n_samples, int32_t units, int32_t uni
 // -------------------------------------------------------------------------------------------------
 // map_relative_coordinates_to_unit_cell   utils/basis_transformations.py:95-119
 // -------------------------------------------------------------------------------------------------
-__global__ void wrap_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+__global__ void wrap_kernel(const float* x, float* out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = wrap_unit(x[i]);
@@ -80,11 +80,11 @@ __device__ __forceinline__ float pc_update_value(float x, float s, float z, floa
 }
 
 template <int D>
-__global__ void pc_coordinates_update_kernel(const float* __restrict__ x, const float* __restrict__ s,
+__global__ void pc_coordinates_update_kernel(const float* x, const float* __restrict__ s,
                                              const float* __restrict__ z, float sw, float sigma,
                                              float nw, int64_t n_samples, int32_t n_atoms,
                                              uint64_t seed, uint32_t step_id,
-                                             uint64_t sample_offset, float* __restrict__ out) {
+                                             uint64_t sample_offset, float* out) {
   const int64_t total = n_samples * n_atoms;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -107,13 +107,14 @@ __global__ void pc_coordinates_update_kernel(const float* __restrict__ x, const 
   }
 }
 
-// Lattice update, generators/langevin_generator.py:485-490 (no wrap).  One thread per (sample, 3-block).
-__global__ void pc_lattice_update_kernel(const float* __restrict__ l, const float* __restrict__ s,
+// Lattice update, generators/langevin_generator.py:485-490 (no wrap).  One thread per (sample, Philox block of 4),
+// the same block layout as draw_kernel with units = 1, unit_size = n_lp.
+__global__ void pc_lattice_update_kernel(const float* l, const float* __restrict__ s,
                                          const float* __restrict__ z, float sw, float sigma_n, float nw,
                                          int64_t n_samples, int32_t n_lp, uint64_t seed,
                                          uint32_t step_id, uint64_t sample_offset,
-                                         float* __restrict__ out) {
-  const int32_t units = (n_lp + 2) / 3;
+                                         float* out) {
+  const int32_t units = (n_lp + 3) / 4;
   const int64_t total = n_samples * units;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -125,8 +126,8 @@ __global__ void pc_lattice_update_kernel(const float* __restrict__ l, const floa
                              B200MD_DRAW_LATTICE_NORMAL);
       normal4(p, zz);
     }
-    for (int d = 0; d < 3; ++d) {
-      int c = unit * 3 + d;
+    for (int d = 0; d < 4; ++d) {
+      int c = unit * 4 + d;
       if (c >= n_lp) break;
       int64_t i = smp * n_lp + c;
       float zv = (z != nullptr) ? z[i] : zz[d];
@@ -142,13 +143,13 @@ __global__ void pc_lattice_update_kernel(const float* __restrict__ l, const floa
 // -------------------------------------------------------------------------------------------------
 constexpr int kMaxClasses = 32;
 
-__global__ void atom_types_update_kernel(const float* __restrict__ logits, const int64_t* __restrict__ a_in,
+__global__ void atom_types_update_kernel(const float* __restrict__ logits, const int64_t* a_in,
                                          const float* __restrict__ q, const float* __restrict__ qbar,
                                          const float* __restrict__ qbar_tm1,
                                          const float* __restrict__ gumbel, const float* __restrict__ binary,
                                          int32_t flags, float eps, int32_t n_atoms, int32_t C,
                                          uint64_t seed, uint32_t step_id, uint64_t sample_offset,
-                                         int64_t* __restrict__ a_out, float* __restrict__ probs_out,
+                                         int64_t* a_out, float* __restrict__ probs_out,
                                          int32_t* __restrict__ status) {
   extern __shared__ unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);  // [3][C*C]
@@ -463,7 +464,7 @@ int b200md_draw_gumbel(float* out, int64_t n_samples, int32_t units, int32_t uni
 int b200md_wrap_to_unit_cell(const float* x, float* out, int64_t n, b200md_stream_t stream) {
   if (n < 0 || (n > 0 && (!x || !out))) return B200MD_ERR_INVALID_ARGUMENT;
   if (n == 0) return B200MD_OK;
-  wrap_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); wrap_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, out, n); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -478,10 +479,13 @@ int b200md_pc_coordinates_update(const float* x, const float* s, const float* z,
   const int64_t total = n_samples * n_atoms;
   const unsigned g = grid_for(total, 256);
   cudaStream_t st = as_stream(stream);
-  switch (D) {
-    case 1: pc_coordinates_update_kernel<1><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
-    case 2: pc_coordinates_update_kernel<2><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
-    default: pc_coordinates_update_kernel<3><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+  {
+    ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
+    switch (D) {
+      case 1: pc_coordinates_update_kernel<1><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+      case 2: pc_coordinates_update_kernel<2><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+      default: pc_coordinates_update_kernel<3><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
+    }
   }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
@@ -493,9 +497,9 @@ int b200md_pc_lattice_update(const float* l, const float* s, const float* z, flo
                              b200md_stream_t stream) {
   if (!l || !s || !l_out || n_samples < 0 || n_lp <= 0) return B200MD_ERR_INVALID_ARGUMENT;
   if (n_samples == 0) return B200MD_OK;
-  const int64_t total = n_samples * ((n_lp + 2) / 3);
-  pc_lattice_update_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
-      l, s, z, score_weight, sigma_n, noise_weight, n_samples, n_lp, seed, step_id, sample_offset, l_out);
+  const int64_t total = n_samples * ((n_lp + 3) / 4);
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, as_stream(stream)); pc_lattice_update_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
+      l, s, z, score_weight, sigma_n, noise_weight, n_samples, n_lp, seed, step_id, sample_offset, l_out); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -517,9 +521,9 @@ int b200md_atom_types_update(const float* logits, const int64_t* atom_types, con
   if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(atom_types_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  atom_types_update_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, as_stream(stream)); atom_types_update_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
       logits, atom_types, q, q_bar, q_bar_tm1, gumbel, binary, flags, small_epsilon, n_atoms, n_classes,
-      seed, step_id, sample_offset, atom_types_out, probs_out, status);
+      seed, step_id, sample_offset, atom_types_out, probs_out, status); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -534,9 +538,9 @@ int b200md_repaint(float* x, int64_t* atom_types, const float* x0_known, const i
     return B200MD_ERR_INVALID_ARGUMENT;
   if (n_samples == 0 || n_constrained == 0) return B200MD_OK;
   const int64_t total = n_samples * n_constrained;
-  repaint_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, as_stream(stream)); repaint_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
       x, atom_types, x0_known, a0_known, constrained_indices, n_constrained, sigma_i, q_bar_i, z, u,
-      n_samples, n_atoms, D, n_classes, seed, step_id, sample_offset);
+      n_samples, n_atoms, D, n_classes, seed, step_id, sample_offset); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -545,7 +549,7 @@ int b200md_wrapped_gaussian_score_f32(const float* u, const float* sigma, int64_
                                       float* out, b200md_stream_t stream) {
   if (n < 0 || kmax < 0 || (n > 0 && (!u || !sigma || !out))) return B200MD_ERR_INVALID_ARGUMENT;
   if (n == 0) return B200MD_OK;
-  wrapped_gaussian_score_kernel<float><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out);
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); wrapped_gaussian_score_kernel<float><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -553,7 +557,7 @@ int b200md_wrapped_gaussian_score_f64(const double* u, const double* sigma, int6
                                       double* out, b200md_stream_t stream) {
   if (n < 0 || kmax < 0 || (n > 0 && (!u || !sigma || !out))) return B200MD_ERR_INVALID_ARGUMENT;
   if (n == 0) return B200MD_OK;
-  wrapped_gaussian_score_kernel<double><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out);
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); wrapped_gaussian_score_kernel<double><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -569,13 +573,13 @@ int b200md_segment_reduce(const float* data, const int64_t* segment_ids, int64_t
   if (mean) cudaMemsetAsync(scratch_counts, 0, sizeof(float) * num_segments, st);
   if (n_elements > 0) {
     if (!data || !segment_ids) return B200MD_ERR_INVALID_ARGUMENT;
-    segment_scatter_kernel<<<grid_for(n_elements * n_features, 256), 256, 0, st>>>(
-        data, segment_ids, n_elements, n_features, out, mean ? scratch_counts : nullptr);
+    { ProfileScope ps__(B200MD_KERNEL_OTHER, st); segment_scatter_kernel<<<grid_for(n_elements * n_features, 256), 256, 0, st>>>(
+        data, segment_ids, n_elements, n_features, out, mean ? scratch_counts : nullptr); }
     B200MD_CHECK_LAUNCH();
   }
   if (mean) {
-    segment_mean_finish_kernel<<<grid_for(num_segments * n_features, 256), 256, 0, st>>>(
-        out, scratch_counts, num_segments, n_features);
+    { ProfileScope ps__(B200MD_KERNEL_OTHER, st); segment_mean_finish_kernel<<<grid_for(num_segments * n_features, 256), 256, 0, st>>>(
+        out, scratch_counts, num_segments, n_features); }
     B200MD_CHECK_LAUNCH();
   }
   return B200MD_OK;

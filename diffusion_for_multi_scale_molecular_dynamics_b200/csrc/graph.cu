@@ -302,13 +302,13 @@ int launch_egnn_graph(const float* x_rel, const float* lattice, float clip_min, 
   const float rc2 = rc * rc;  // radial_cutoff**2 on a float32 tensor (neighbors.py:103,172)
   int threads = N >= 256 ? 256 : (N >= 64 ? 128 : 64);
   size_t smem = (size_t)(3 * N + 81) * sizeof(float);
-  egnn_graph_count_kernel<<<(unsigned)B, threads, smem, st>>>(x_rel, lattice, clip_min, rc, rc2, N, W,
-                                                              fully_connected, bitmask, deg, struct_total, status);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, st); egnn_graph_count_kernel<<<(unsigned)B, threads, smem, st>>>(x_rel, lattice, clip_min, rc, rc2, N, W,
+                                                              fully_connected, bitmask, deg, struct_total, status); }
   B200MD_CHECK_LAUNCH();
-  egnn_graph_scan_kernel<<<1, 1024, 0, st>>>(struct_total, B, capacity, struct_off, n_edges, status);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, st); egnn_graph_scan_kernel<<<1, 1024, 0, st>>>(struct_total, B, capacity, struct_off, n_edges, status); }
   B200MD_CHECK_LAUNCH();
-  egnn_graph_fill_kernel<<<(unsigned)B, threads, (size_t)(N + 1) * sizeof(int), st>>>(
-      bitmask, deg, struct_off, n_edges, N, W, B, row_ptr, edge_src, edge_dst);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, st); egnn_graph_fill_kernel<<<(unsigned)B, threads, (size_t)(N + 1) * sizeof(int), st>>>(
+      bitmask, deg, struct_off, n_edges, N, W, B, row_ptr, edge_src, edge_dst); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -332,9 +332,9 @@ int b200md_radius_graph_count(const float* positions, const float* cell, int32_t
   const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(radius_graph_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  radius_graph_count_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); radius_graph_count_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
       positions, cell, positions_are_relative, radial_cutoff, radial_cutoff * radial_cutoff, n_atoms, mode,
-      counts, edges_per_structure, status);
+      counts, edges_per_structure, status); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -356,9 +356,9 @@ int b200md_radius_graph_fill(const float* positions, const float* cell, int32_t 
   if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(radius_graph_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  radius_graph_fill_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); radius_graph_fill_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
       positions, cell, positions_are_relative, radial_cutoff * radial_cutoff, n_atoms, mode, offsets,
-      node_index_offset, src_out, dst_out, shifts_out, edge_batch);
+      node_index_offset, src_out, dst_out, shifts_out, edge_batch); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }

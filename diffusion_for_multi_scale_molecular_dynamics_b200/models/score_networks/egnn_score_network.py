@@ -96,6 +96,19 @@ class EGNNScoreNetwork(ScoreNetwork):
         self._workspace: Optional[torch.Tensor] = None
         self._workspace_key = None
         self._fuse_mask_logit = False
+        self._n_edges: Optional[torch.Tensor] = None  # device int64[1]: edges of the last graph built by forward()
+
+    def last_number_of_edges(self) -> int:
+        """Total number of directed edges of the graph used by the last ``forward`` (one host sync)."""
+        return 0 if self._n_edges is None else int(self._n_edges.item())
+
+    def last_edge_kernel_name(self) -> str:
+        """Which edge-MLP implementation ``kernel_impl`` resolves to for this configuration."""
+        cfg = self._config()
+        resolved = _cabi.lib().b200md_egnn_resolve_impl(ctypes.byref(cfg), int(self.kernel_impl))
+        return {_cabi.IMPL_FFMA: "egnn_edge_kernel (fp32 FFMA tiles)",
+                _cabi.IMPL_TCGEN05: "egnn_edge_tc_kernel (tcgen05 3xTF32, fp32 accumulate in TMEM)"}.get(
+                    resolved, f"unsupported ({resolved})")
 
     # ---- reference helpers kept for API compatibility ----------------------------------------------------
     @staticmethod
@@ -230,9 +243,12 @@ class EGNNScoreNetwork(ScoreNetwork):
         logits = torch.empty(batch_size, number_of_atoms, num_classes, dtype=torch.float32, device=device)
         scores = torch.empty(batch_size, number_of_atoms, 3, dtype=torch.float32, device=device)
         status = self.device_status(device)
+        if self._n_edges is None or self._n_edges.device != device:
+            self._n_edges = torch.zeros(1, dtype=torch.int64, device=device)
         _cabi.check(_cabi.lib().b200md_egnn_forward(
             ctypes.byref(cfg), _cabi.ptr(packed), _cabi.ptr(a), _cabi.ptr(x), _cabi.ptr(lattice), _cabi.ptr(sigma),
             batch_size, number_of_atoms, int(self._fuse_mask_logit), _cabi.ptr(logits), _cabi.ptr(scores),
-            _cabi.ptr(workspace), workspace.numel(), capacity, None, _cabi.ptr(status), int(self.kernel_impl),
+            _cabi.ptr(workspace), workspace.numel(), capacity, _cabi.ptr(self._n_edges), _cabi.ptr(status),
+            int(self.kernel_impl),
             _cabi.stream_ptr(device)))
         return AXL(A=logits, X=scores, L=torch.zeros_like(composition.L))

@@ -53,6 +53,19 @@ int b200md_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t b200md_launch_count(void);
 
+/* Optional in-stream kernel timing (bench.py's roofline leg): when enabled every launch is bracketed by a pair of
+ * CUDA events recorded on the launch stream; b200md_profile_collect synchronises them, adds the elapsed
+ * milliseconds and launch counts per kernel class into the caller's HOST arrays (length n_classes >=
+ * B200MD_KERNEL_CLASSES) and clears the record. */
+#define B200MD_KERNEL_GRAPH 0   /* radius graph: count / scan / fill */
+#define B200MD_KERNEL_NODE 1    /* EGNN node kernel: embed, node MLP, read-out */
+#define B200MD_KERNEL_EDGE 2    /* EGNN edge kernel: message + coordinate MLPs, segmented reduction */
+#define B200MD_KERNEL_UPDATE 3  /* predictor/corrector coordinate, atom-type, lattice, repaint updates */
+#define B200MD_KERNEL_OTHER 4   /* noise draws, wrap, wrapped-Gaussian score, segment reductions, packing */
+#define B200MD_KERNEL_CLASSES 5
+int b200md_profile_enable(int32_t on);
+int b200md_profile_collect(double* ms_by_class_host, int64_t* launches_by_class_host, int32_t n_classes);
+
 /* ------------------------------------------------------------------------------------------------
  * Counter-based noise (replaces the CPU torch.rand/randn + H2D copy of
  * generators/langevin_generator.py:92-111 and generators/trajectory_initializer.py:109-119).
@@ -256,6 +269,10 @@ int64_t b200md_egnn_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_sam
 #define B200MD_IMPL_AUTO 0
 #define B200MD_IMPL_FFMA 1    /* fp32 CUDA-core tiles */
 #define B200MD_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma tiles, fp32 accumulate in TMEM */
+
+/* The implementation B200MD_IMPL_AUTO resolves to for this configuration (B200MD_IMPL_FFMA or B200MD_IMPL_TCGEN05),
+ * or a negative error when `impl` is not available for it. */
+int b200md_egnn_resolve_impl(const b200md_egnn_config* cfg, int32_t impl);
 
 /* atom_types [B,N] int64, x [B,N,3] in [0,1), lattice [B,6], sigma [B] ->
  * logits_out [B,N,C] (C = num_atom_types+1; MASK logit = -inf when mask_logit_to_neg_inf),
