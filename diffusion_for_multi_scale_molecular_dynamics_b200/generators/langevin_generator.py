@@ -43,8 +43,7 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
     _HOOKS = ("_draw_coordinates_gaussian_sample", "_draw_lattice_gaussian_sample", "_draw_gumbel_sample",
               "_draw_binary_sample", "_get_model_predictions", "_relative_coordinates_update",
               "_relative_coordinates_update_predictor_step", "_relative_coordinates_update_corrector_step",
-              "_atom_types_update", "_get_updated_atom_types_for_one_transition_per_step",
-              "_adjust_atom_types_probabilities_for_greedy_sampling", "_lattice_parameters_update",
+              "_atom_types_update", "_lattice_parameters_update",
               "_lattice_parameters_update_predictor_step", "_lattice_parameters_update_corrector_step",
               "_get_coordinates_corrector_step_size", "_get_lattice_parameters_corrector_step_size",
               "predictor_step", "corrector_step")
@@ -455,8 +454,8 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
         for name in self._HOOKS:
             if name in self.__dict__:  # instance-level patch (e.g. unittest.mock.patch.object)
                 return True
-            implementation = getattr(type(self), name)
-            if not any(c.__dict__.get(name) is implementation for c in known):
+            implementation = getattr(type(self), name, None)
+            if implementation is None or not any(c.__dict__.get(name) is implementation for c in known):
                 return True
         return False
 
