@@ -288,26 +288,68 @@ def test_egnn_state_dict_is_reference_compatible():
     assert torch.equal(own["projection_matrices"], reference["projection_matrices"])
 
 
-@pytest.mark.parametrize("num_atom_types,N,B,length", [(1, 64, 6, 10.86), (2, 64, 4, 11.084), (1, 216, 2, 16.29)])
-def test_egnn_forward_production_width_against_oracle(cuda_device, num_atom_types, N, B, length):
-    """Production widths of the reference's Si/SiGe configs (256 x 4 hidden layers, 4 E_GCL, rc = 7.5, mean agg)."""
-    hp = dict(num_atom_types=num_atom_types, edges="radial_cutoff", radial_cutoff=7.5, n_layers=4,
-              message_n_hidden_dimensions=4, message_hidden_dimensions_size=256, node_n_hidden_dimensions=4,
-              node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4, coordinate_hidden_dimensions_size=256)
-    torch.manual_seed(5)
+def run_against_oracle(cuda_device, hp, N, B, length, impl, seed=5):
+    torch.manual_seed(seed)
     net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.to(cuda_device)
+    net.kernel_impl = impl
+    num_atom_types = hp["num_atom_types"]
     x = torch.rand(B, N, 3)
     a = torch.randint(0, num_atom_types + 1, (B, N))
     lattice = torch.zeros(B, 6)
     lattice[:, :3] = length
     sigma = torch.rand(B, 1) * 0.4 + 0.005
     out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
-    full = dict(residual=True, attention=False, normalize=False, tanh=False, coords_agg="mean", message_agg="mean", **hp)
+    full = dict(residual=True, attention=False, normalize=False, tanh=False, coords_agg="mean", message_agg="mean")
+    full.update(hp)
     logits, score = oracle.egnn_score_forward(sd, full, a, x, lattice, sigma)
     assert_rel(out.X, score, 1e-5, "score", floor=SCORE_CANCELLATION_FLOOR)
     assert_rel(out.A, logits, 1e-5, "logits")
+    return net
+
+
+PRODUCTION = dict(edges="radial_cutoff", radial_cutoff=7.5, n_layers=4, message_n_hidden_dimensions=4,
+                  message_hidden_dimensions_size=256, node_n_hidden_dimensions=4, node_hidden_dimensions_size=256,
+                  coordinate_n_hidden_dimensions=4, coordinate_hidden_dimensions_size=256)
+
+
+@pytest.mark.parametrize("impl", [_cabi.IMPL_FFMA, _cabi.IMPL_TCGEN05], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("num_atom_types,N,B,length", [(1, 64, 6, 10.86), (2, 64, 4, 11.084), (1, 216, 2, 16.29)])
+def test_egnn_forward_production_width_against_oracle(cuda_device, num_atom_types, N, B, length, impl):
+    """Production widths of the reference's Si/SiGe configs (256 x 4 hidden layers, 4 E_GCL, rc = 7.5, mean agg),
+    with the fp32 CUDA-core edge kernel and with the tcgen05 3xTF32 edge kernel."""
+    net = run_against_oracle(cuda_device, dict(num_atom_types=num_atom_types, **PRODUCTION), N, B, length, impl)
+    assert ("tcgen05" in net.last_edge_kernel_name()) == (impl == _cabi.IMPL_TCGEN05)
+
+
+@pytest.mark.parametrize("hp", [
+    dict(message_hidden_dimensions_size=96, coordinate_hidden_dimensions_size=160, message_n_hidden_dimensions=2,
+         coordinate_n_hidden_dimensions=0, node_hidden_dimensions_size=64, n_layers=2, normalize=True, tanh=True,
+         coords_agg="sum", message_agg="sum", number_of_bloch_wave_shells=2),
+    dict(message_hidden_dimensions_size=32, coordinate_hidden_dimensions_size=32, message_n_hidden_dimensions=0,
+         coordinate_n_hidden_dimensions=1, node_hidden_dimensions_size=32, n_layers=3, residual=False),
+    dict(message_hidden_dimensions_size=256, coordinate_hidden_dimensions_size=64, message_n_hidden_dimensions=1,
+         coordinate_n_hidden_dimensions=3, node_hidden_dimensions_size=128, n_layers=1, edges="fully_connected"),
+], ids=["96x160-norm-tanh-sum", "32-no-hidden-message", "256to64-fully-connected"])
+def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp):
+    """The tensor-core edge kernel over its whole supported envelope: any widths that are multiples of 32 (<= 256),
+    any number of hidden layers, normalize / tanh, sum or mean aggregation, both edge modes."""
+    full = dict(num_atom_types=2, edges="radial_cutoff", radial_cutoff=3.1)
+    full.update(hp)
+    if full["edges"] == "fully_connected":
+        full.pop("radial_cutoff")
+    net = run_against_oracle(cuda_device, full, 40, 5, 7.0, _cabi.IMPL_TCGEN05, seed=8)
+    assert "tcgen05" in net.last_edge_kernel_name()
+
+
+def test_tcgen05_unsupported_configuration_is_refused(cuda_device):
+    g = sub_dict(load_golden("egnn_forward"), "default_fc")  # message width 16: not a multiple of 32
+    net = make_network("default_fc", sub_dict(g, "sd"), cuda_device)
+    assert "FFMA" in net.last_edge_kernel_name()
+    net.kernel_impl = _cabi.IMPL_TCGEN05
+    with pytest.raises(_cabi.B200MDError):
+        net(network_batch(g["a"], g["x"], g["l"], g["sigma"], cuda_device), conditional=False)
 
 
 def test_egnn_input_validation(cuda_device):
