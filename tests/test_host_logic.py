@@ -1,0 +1,169 @@
+"""CPU: host-side mirror of the reference interface -- noise tables, dataclasses, Bloch vectors, generator plumbing."""
+import dataclasses
+from unittest import mock
+
+import pytest
+import torch
+
+from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.constrained_langevin_generator import \
+    ConstrainedLangevinGenerator
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.instantiate_generator import instantiate_generator
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.langevin_generator import LangevinGenerator
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.load_sampling_parameters import \
+    load_sampling_parameters
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.predictor_corrector_axl_generator import \
+    PredictorCorrectorSamplingParameters
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.sampling_constraint import (
+    SamplingConstraint, read_sampling_constraint, write_sampling_constraint)
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.trajectory_initializer import (
+    FullRandomTrajectoryInitializer, instantiate_trajectory_initializer)
+from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.egnn_score_network import (
+    EGNNScoreNetwork, EGNNScoreNetworkParameters)
+from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.score_network_factory import (
+    SCORE_NETWORKS_BY_ARCH, create_score_network, create_score_network_parameters)
+from diffusion_for_multi_scale_molecular_dynamics_b200.namespace import AXL
+from diffusion_for_multi_scale_molecular_dynamics_b200.noise_schedulers.noise_parameters import NoiseParameters
+from diffusion_for_multi_scale_molecular_dynamics_b200.noise_schedulers.noise_scheduler import NoiseScheduler
+from tests.conftest import load_golden, sub_dict
+from tests.egnn_variants import EGNN_VARIANTS
+
+
+@pytest.mark.parametrize("tag,kwargs,C", [
+    ("exp_T10_C2", dict(total_time_steps=10), 2),
+    ("lin_T7_C3", dict(total_time_steps=7, schedule_type="linear", sigma_min=1e-4, sigma_max=0.2,
+                       corrector_step_epsilon=2.5e-8), 3),
+    ("exp_T1000_C2", dict(total_time_steps=1000), 2),
+])
+def test_noise_scheduler_tables_are_bit_identical_to_the_reference(tag, kwargs, C):
+    golden = sub_dict(load_golden("noise_tables"), tag)
+    noise, langevin = NoiseScheduler(NoiseParameters(**kwargs), num_classes=C).get_all_sampling_parameters()
+    for field in ("time", "sigma", "sigma_squared", "g", "g_squared", "beta", "alpha_bar", "q_matrix", "q_bar_matrix",
+                  "q_bar_tm1_matrix"):
+        assert torch.equal(getattr(noise, field), golden[field]), field
+    assert torch.equal(langevin.epsilon, golden["epsilon"])
+    assert torch.equal(langevin.sqrt_2_epsilon, golden["sqrt_2_epsilon"])
+
+
+def test_unknown_schedule_is_refused():
+    with pytest.raises(AssertionError):
+        NoiseParameters(total_time_steps=5, schedule_type="cosine")
+
+
+@pytest.mark.parametrize("variant", list(EGNN_VARIANTS))
+def test_egnn_module_tree_matches_the_reference_state_dict(variant):
+    """Same parameter names, shapes, and -- for the frozen Bloch / projection tensors -- values."""
+    reference = sub_dict(sub_dict(load_golden("egnn_forward"), variant), "sd")
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**EGNN_VARIANTS[variant]))
+    own = net.state_dict()
+    assert list(own) == list(reference)
+    for key, value in own.items():
+        assert value.shape == reference[key].shape, key
+    assert torch.equal(own["bloch_wave_reciprocal_lattice_vectors"], reference["bloch_wave_reciprocal_lattice_vectors"])
+    assert torch.equal(own["projection_matrices"], reference["projection_matrices"])
+    net.load_state_dict(reference, strict=True)
+
+
+def test_same_seed_gives_the_reference_initial_weights():
+    """Module construction order equals the reference's, so torch.manual_seed reproduces its random init."""
+    reference = sub_dict(sub_dict(load_golden("egnn_forward"), "radial_sige"), "sd")
+    torch.manual_seed(100)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**EGNN_VARIANTS["radial_sige"]))
+    for key, value in net.state_dict().items():
+        assert torch.equal(value, reference[key]), key
+
+
+def test_score_network_factory():
+    assert SCORE_NETWORKS_BY_ARCH["egnn"] is EGNNScoreNetwork
+    params = create_score_network_parameters(dict(architecture="egnn", n_layers=2), dict(num_atom_types=2, unrelated=1))
+    assert isinstance(params, EGNNScoreNetworkParameters) and params.num_atom_types == 2 and params.n_layers == 2
+    assert isinstance(create_score_network(params), EGNNScoreNetwork)
+    with pytest.raises(NotImplementedError):
+        create_score_network_parameters(dict(architecture="mace"), dict(num_atom_types=1))
+    with pytest.raises(AssertionError):
+        EGNNScoreNetwork(EGNNScoreNetworkParameters(num_atom_types=1, edges="radial_cutoff"))  # cutoff missing
+    with pytest.raises(AssertionError):
+        EGNNScoreNetwork(EGNNScoreNetworkParameters(num_atom_types=1, edges="fully_connected", radial_cutoff=3.0))
+
+
+def sampling(**kwargs):
+    base = dict(number_of_samples=4, number_of_atoms=8, num_atom_types=1, use_fixed_lattice_parameters=True,
+                cell_dimensions=[5.43, 5.43, 5.43])
+    base.update(kwargs)
+    return PredictorCorrectorSamplingParameters(**base)
+
+
+def test_sampling_parameters_mirror_the_reference_defaults():
+    p = sampling()
+    assert p.algorithm == "predictor_corrector" and p.number_of_corrector_steps == 1 and p.small_epsilon == 1e-8
+    assert p.one_atom_type_transition_per_step and p.atom_type_greedy_sampling
+    assert not p.atom_type_transition_in_corrector and p.sample_batchsize is None
+    assert torch.allclose(p.fixed_lattice_parameters, torch.tensor([5.43, 5.43, 5.43, 0, 0, 0]))
+    with pytest.raises(AssertionError):
+        sampling(cell_dimensions=None)
+    loaded = load_sampling_parameters(dict(algorithm="predictor_corrector", **{
+        k: v for k, v in dataclasses.asdict(p).items() if k not in ("algorithm",)}))
+    assert loaded == p
+    with pytest.raises(AssertionError):
+        load_sampling_parameters(dict(algorithm="ode"))
+
+
+def test_generator_plumbing_without_a_device():
+    noise = NoiseParameters(total_time_steps=5)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(num_atom_types=1))
+    gen = instantiate_generator(sampling(), noise, net)
+    assert type(gen) is LangevinGenerator and isinstance(gen.trajectory_initializer, FullRandomTrajectoryInitializer)
+    assert gen.num_classes == 2 and gen.masked_atom_type_index == 1 and gen.number_of_discretization_steps == 5
+    assert not gen._hooks_overridden()
+    with mock.patch.object(gen, "_draw_gumbel_sample", return_value=None):
+        assert gen._hooks_overridden()  # an injected hook must force the step-by-step loop
+    assert not gen._hooks_overridden()
+
+    class Tweaked(LangevinGenerator):
+        def _get_coordinates_corrector_step_size(self, index_i, sigma_i, model_predictions_i, z):
+            return 0.5
+
+    assert Tweaked(noise, sampling(), net)._hooks_overridden()
+    constraint = SamplingConstraint(elements=["Si"], constrained_relative_coordinates=torch.rand(3, 3),
+                                    constrained_atom_types=torch.zeros(3, dtype=torch.long))
+    constrained = instantiate_generator(sampling(), noise, net, sampling_constraints=constraint)
+    assert type(constrained) is ConstrainedLangevinGenerator and not constrained._hooks_overridden()
+    assert torch.equal(constrained.constraint_indices, torch.arange(3))
+    with pytest.raises(NotImplementedError):
+        instantiate_generator(dataclasses.replace(sampling(), algorithm="ode"), noise, net)
+    with pytest.raises(AssertionError):
+        gen.predictor_step(AXL(A=torch.zeros(1, 8), X=torch.zeros(1, 8, 3), L=torch.zeros(1, 6)), 0, None)
+    with pytest.raises(AssertionError):
+        gen.sample_from_noisy_composition(AXL(A=None, X=torch.zeros(1, 8, 3), L=None), 2, 2)
+    with pytest.raises(_cabi.B200MDError):  # no CPU path
+        gen.sample(2, torch.device("cpu"))
+    with pytest.raises(AssertionError):
+        LangevinGenerator(noise, sampling(record_samples_corrector_steps=True), net)
+
+
+def test_sampling_constraint_validation_and_round_trip(tmp_path):
+    constraint = SamplingConstraint(elements=["Si", "Ge"], constrained_relative_coordinates=torch.rand(2, 3),
+                                    constrained_atom_types=torch.tensor([0, 1]),
+                                    constrained_indices=torch.tensor([4, 1]))
+    write_sampling_constraint(constraint, tmp_path / "c.pt")
+    again = read_sampling_constraint(tmp_path / "c.pt")
+    assert torch.equal(again.constrained_relative_coordinates, constraint.constrained_relative_coordinates)
+    assert torch.equal(again.constrained_indices, constraint.constrained_indices) and again.elements == ["Si", "Ge"]
+    with pytest.raises(AssertionError):
+        SamplingConstraint(elements=["Si"], constrained_relative_coordinates=torch.rand(2, 3),
+                           constrained_atom_types=torch.tensor([0, 1]))  # type 1 not in elements
+    with pytest.raises(AssertionError):
+        SamplingConstraint(elements=["Si"], constrained_relative_coordinates=torch.rand(2, 3).double(),
+                           constrained_atom_types=torch.tensor([0, 0]))
+
+
+def test_trajectory_initializer_factory(tmp_path):
+    p = sampling()
+    assert isinstance(instantiate_trajectory_initializer(p), FullRandomTrajectoryInitializer)
+    start = AXL(A=torch.zeros(4, 8, dtype=torch.long), X=torch.rand(4, 8, 3), L=torch.zeros(4, 6))
+    torch.save({"noisy_axl": start, "start_time_step_index": 3}, tmp_path / "start.pt")
+    init = instantiate_trajectory_initializer(p, str(tmp_path / "start.pt"))
+    assert init.create_start_time_step_index(1000) == 3 and init.create_end_time_step_index() == 0
+    assert torch.equal(init.initialize(4, torch.device("cpu")).X, start.X)
+    with pytest.raises(AssertionError):
+        init.initialize(5, torch.device("cpu"))
