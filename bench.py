@@ -208,6 +208,8 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     hp = network_hyper_parameters(workload)
     torch.manual_seed(1234)
     network = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp)).to(device)
+    network.kernel_impl = {"auto": _cabi.IMPL_AUTO, "ffma": _cabi.IMPL_FFMA, "tf32x3": _cabi.IMPL_TCGEN05,
+                           "f16x3": _cabi.IMPL_TCGEN05_F16X3}[args.kernels]
     noise = NoiseParameters(total_time_steps=TOTAL_TIME_STEPS)
     sampling = PredictorCorrectorSamplingParameters(
         number_of_samples=samples * world, number_of_atoms=atoms, num_atom_types=num_atom_types,
@@ -374,6 +376,8 @@ def main():
     parser.add_argument("--samples", type=int, default=None, help="samples per GPU (default: the workload's)")
     parser.add_argument("--cpu-samples", type=int, default=32, help="structures per CPU-baseline step")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--kernels", choices=["auto", "ffma", "tf32x3", "f16x3"], default="auto",
+                        help="edge/node MLP implementation (auto = what the library picks for the configuration)")
     args = parser.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -28,6 +28,7 @@ STATUS_EDGE_OVERFLOW = 8
 STATUS_MASK_REMAINS = 16
 STATUS_BAD_LOGITS = 32
 STATUS_SIGMA_OUT_OF_RANGE = 64
+STATUS_TC_RANGE = 128
 
 STATUS_MESSAGES = {
     STATUS_X_OUT_OF_RANGE: "All components of the relative coordinates are expected to be in [0,1).",
@@ -39,6 +40,8 @@ STATUS_MESSAGES = {
     "invalid input.",
     STATUS_BAD_LOGITS: "Logits are pathological: the probabilities do not sum to one.",
     STATUS_SIGMA_OUT_OF_RANGE: "All values of sigma should be larger than zero.",
+    STATUS_TC_RANGE: "An activation exceeded the fp16 range of the 3xFP16 tensor-core kernels; set "
+    "kernel_impl = IMPL_TCGEN05 (3xTF32) for this network.",
 }
 
 DRAW_COORD_NORMAL, DRAW_GUMBEL, DRAW_BINARY, DRAW_LATTICE_NORMAL = 0, 1, 2, 3
@@ -46,7 +49,7 @@ DRAW_INIT_UNIFORM, DRAW_REPAINT_NORMAL, DRAW_REPAINT_UNIFORM, DRAW_REPAINT_INIT 
 
 ATOM_GREEDY, ATOM_ONE_TRANSITION, ATOM_LAST_STEP = 1, 2, 4
 GRAPH_UNIQUE_PAIRS, GRAPH_PER_IMAGE = 0, 1
-IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05, IMPL_TCGEN05_F16X3 = 0, 1, 2, 3
 
 EGNN_RESIDUAL, EGNN_ATTENTION, EGNN_NORMALIZE, EGNN_TANH = 1, 2, 4, 8
 EGNN_COORDS_MEAN, EGNN_MESSAGE_MEAN, EGNN_RADIAL_CUTOFF, EGNN_KEEP_DUPLICATES = 16, 32, 64, 128

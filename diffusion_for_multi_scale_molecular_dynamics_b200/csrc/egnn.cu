@@ -56,11 +56,17 @@ int build_layout(const b200md_egnn_config& cfg, EgnnLayout& lay) {
   }
   lay.readout_w = take((int64_t)lay.C * H);
   lay.readout_b = take(lay.C);
-  lay.tc_base = o;
-  lay.tc_layer_stride = 0;
-  if (tc_edge_supported(cfg)) {
-    lay.tc_layer_stride = tc_packed_floats(cfg);
-    o = align64(o + lay.tc_layer_stride * cfg.n_layers);
+  lay.tc_edge_base = o;
+  lay.tc_edge_stride = 0;
+  if (tc_edge_supported(cfg, 0)) {
+    lay.tc_edge_stride = align64(tc_edge_packed_floats(cfg));
+    o = align64(o + lay.tc_edge_stride * cfg.n_layers);
+  }
+  lay.tc_node_base = o;
+  lay.tc_node_stride = 0;
+  if (tc_node_supported(cfg, 0)) {
+    lay.tc_node_stride = align64(tc_node_packed_floats(cfg));
+    o = align64(o + lay.tc_node_stride * cfg.n_layers);
   }
   lay.total = o;
   return B200MD_OK;
@@ -537,13 +543,21 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
     if (e2 != cudaSuccess) return set_cuda_error(e2);
     attrs_set = true;
   }
+  // B200MD_IMPL_TCGEN05: 3xTF32 tensor-core kernels (any widths that are multiples of 32); B200MD_IMPL_TCGEN05_F16X3:
+  // 3xFP16 (multiples of 64); AUTO prefers F16X3, then TF32, then the CUDA-core kernels.
   bool use_tc = false;
-  if (impl == B200MD_IMPL_TCGEN05) {
-    if (!tc_edge_supported(cfg)) return B200MD_ERR_UNSUPPORTED;
+  int precision = 0;
+  if (impl == B200MD_IMPL_TCGEN05 || impl == B200MD_IMPL_TCGEN05_F16X3) {
+    precision = (impl == B200MD_IMPL_TCGEN05_F16X3) ? 1 : 0;
+    if (!tc_edge_supported(cfg, precision)) return B200MD_ERR_UNSUPPORTED;
     use_tc = true;
   } else if (impl == B200MD_IMPL_AUTO) {
-    use_tc = tc_edge_supported(cfg);
+    if (tc_edge_supported(cfg, 1) && tc_node_supported(cfg, 1)) { use_tc = true; precision = 1; }
+    else if (tc_edge_supported(cfg, 0)) { use_tc = true; precision = 0; }
+  } else if (impl != B200MD_IMPL_FFMA) {
+    return B200MD_ERR_INVALID_ARGUMENT;
   }
+  const bool use_tc_node = use_tc && tc_node_supported(cfg, precision);
   const int64_t BN = B * N;
   const bool radial = cfg.flags & B200MD_EGNN_RADIAL_CUTOFF;
   int rc = launch_egnn_graph(x, lattice, cfg.lattice_clip_min, cfg.radial_cutoff, B, N, radial ? 0 : 1,
@@ -566,15 +580,25 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
   na.readout_w = lay.readout_w; na.readout_b = lay.readout_b;
   const unsigned node_grid = (unsigned)ceil_div64(BN, kTMN);
 
+  NodeCall nc{};
+  nc.mask_logit = mask_logit; nc.atom_types = atom_types; nc.x_rel = x; nc.sigma = sigma; nc.sigma_scalar = sigma_scalar;
+  nc.ws = &ws; nc.logits_out = logits_out; nc.score_out = score_out; nc.status = status; nc.n_nodes = BN; nc.n_atoms = N;
+
   // call 0: embedding + uplift + partial products of layer 0
-  na.do_embed = 1; na.do_update = 0; na.do_pq = 1; na.do_readout = 0;
-  na.msg_wa_t = lay.layer[0].msg_wa_t; na.msg_wb_t = lay.layer[0].msg_wb_t; na.msg_b0 = lay.layer[0].msg_b0;
-  { ProfileScope ps__(B200MD_KERNEL_NODE, st); egnn_node_kernel<<<node_grid, kThreads, node_smem_bytes(), st>>>(na); }
-  B200MD_CHECK_LAUNCH();
+  if (use_tc_node) {
+    nc.embed = 1; nc.update_layer = -1; nc.pq_layer = 0; nc.readout = 0;
+    rc = tc_launch_node(cfg, lay, packed, nc, precision, st);
+    if (rc != B200MD_OK) return rc;
+  } else {
+    na.do_embed = 1; na.do_update = 0; na.do_pq = 1; na.do_readout = 0;
+    na.msg_wa_t = lay.layer[0].msg_wa_t; na.msg_wb_t = lay.layer[0].msg_wb_t; na.msg_b0 = lay.layer[0].msg_b0;
+    { ProfileScope ps__(B200MD_KERNEL_NODE, st); egnn_node_kernel<<<node_grid, kThreads, node_smem_bytes(), st>>>(na); }
+    B200MD_CHECK_LAUNCH();
+  }
 
   for (int l = 0; l < cfg.n_layers; ++l) {
     if (use_tc) {
-      rc = tc_launch_edge_layer(cfg, lay, l, packed, ws, st);
+      rc = tc_launch_edge_layer(cfg, lay, l, packed, ws, status, precision, st);
       if (rc != B200MD_OK) return rc;
     } else {
       EdgeArgs ea{};
@@ -592,6 +616,12 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
       B200MD_CHECK_LAUNCH();
     }
     const bool last = (l == cfg.n_layers - 1);
+    if (use_tc_node) {
+      nc.embed = 0; nc.update_layer = l; nc.pq_layer = last ? -1 : l + 1; nc.readout = last ? 1 : 0;
+      rc = tc_launch_node(cfg, lay, packed, nc, precision, st);
+      if (rc != B200MD_OK) return rc;
+      continue;
+    }
     na.do_embed = 0; na.do_update = 1; na.do_pq = last ? 0 : 1; na.do_readout = last ? 1 : 0;
     const EgnnLayerOffsets& L = lay.layer[l];
     na.node_w0_t = L.node_w0_t; na.node_b0 = L.node_b0; na.node_hidden_wt = L.node_hidden_wt;
@@ -673,11 +703,9 @@ int b200md_egnn_pack_weights(const b200md_egnn_config* cfg, const float* const* 
   }
   if (pack_c(p[i++], lay.C * H, 1, packed + lay.readout_w, st)) return B200MD_ERR_CUDA;
   if (pack_c(p[i++], lay.C, 1, packed + lay.readout_b, st)) return B200MD_ERR_CUDA;
-  if (lay.tc_layer_stride > 0) {
-    for (int l = 0; l < cfg->n_layers; ++l) {
-      rc = tc_pack_layer(*cfg, lay, l, packed, st);
-      if (rc != B200MD_OK) return rc;
-    }
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    if (lay.tc_edge_stride > 0 && (rc = tc_edge_pack_layer(*cfg, lay, l, packed, st)) != B200MD_OK) return rc;
+    if (lay.tc_node_stride > 0 && (rc = tc_node_pack_layer(*cfg, lay, l, packed, st)) != B200MD_OK) return rc;
   }
   return B200MD_OK;
 }
@@ -717,8 +745,12 @@ int b200md_egnn_resolve_impl(const b200md_egnn_config* cfg, int32_t impl) {
   int rc = build_layout(*cfg, lay);
   if (rc != B200MD_OK) return rc;
   if (impl == B200MD_IMPL_FFMA) return B200MD_IMPL_FFMA;
-  if (impl == B200MD_IMPL_TCGEN05) return tc_edge_supported(*cfg) ? B200MD_IMPL_TCGEN05 : B200MD_ERR_UNSUPPORTED;
-  if (impl == B200MD_IMPL_AUTO) return tc_edge_supported(*cfg) ? B200MD_IMPL_TCGEN05 : B200MD_IMPL_FFMA;
+  if (impl == B200MD_IMPL_TCGEN05 || impl == B200MD_IMPL_TCGEN05_F16X3)
+    return tc_edge_supported(*cfg, impl == B200MD_IMPL_TCGEN05_F16X3 ? 1 : 0) ? impl : B200MD_ERR_UNSUPPORTED;
+  if (impl == B200MD_IMPL_AUTO) {
+    if (tc_edge_supported(*cfg, 1) && tc_node_supported(*cfg, 1)) return B200MD_IMPL_TCGEN05_F16X3;
+    return tc_edge_supported(*cfg, 0) ? B200MD_IMPL_TCGEN05 : B200MD_IMPL_FFMA;
+  }
   return B200MD_ERR_INVALID_ARGUMENT;
 }
 

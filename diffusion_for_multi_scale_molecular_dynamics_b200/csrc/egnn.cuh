@@ -27,9 +27,10 @@ struct EgnnLayout {
   int64_t bloch, proj, embed_w, embed_b, readout_w, readout_b;
   EgnnLayerOffsets layer[16];
   int64_t total;
-  // tcgen05 images (appended after the fp32 section; see egnn_tc.cu)
-  int64_t tc_base;
-  int64_t tc_layer_stride;
+  // tcgen05 weight images (appended after the fp32 section; see tc_common.cuh): one block per layer for the edge
+  // MLPs (egnn_tc.cu) and one for the node MLPs (egnn_node_tc.cu); stride 0 = that kernel is not available
+  int64_t tc_edge_base, tc_edge_stride;
+  int64_t tc_node_base, tc_node_stride;
 };
 
 int build_layout(const b200md_egnn_config& cfg, EgnnLayout& lay);
@@ -50,11 +51,27 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
                       float* score_out, const EgnnWorkspace& ws, int64_t edge_capacity, int32_t* status,
                       int impl, cudaStream_t st);
 
-// tcgen05 edge kernel (egnn_tc.cu)
-bool tc_edge_supported(const b200md_egnn_config& cfg);
-int64_t tc_packed_floats(const b200md_egnn_config& cfg);
-int tc_pack_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, int layer, float* packed, cudaStream_t st);
+// tcgen05 kernels.  `precision` is tc::kTf32x3 (0) or tc::kF16x3 (1), see tc_common.cuh.
+int tc_sm_count();
+bool tc_edge_supported(const b200md_egnn_config& cfg, int precision);
+int64_t tc_edge_packed_floats(const b200md_egnn_config& cfg);
+int tc_edge_pack_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, int layer, float* packed, cudaStream_t st);
 int tc_launch_edge_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, int layer, const float* packed,
-                         const EgnnWorkspace& ws, cudaStream_t st);
+                         const EgnnWorkspace& ws, int32_t* status, int precision, cudaStream_t st);
+
+// One launch of the node kernel: optionally embed, update layer `update_layer` (-1: none), produce P/Q for layer
+// `pq_layer` (-1: none), read out.
+struct NodeCall {
+  int embed, update_layer, pq_layer, readout, mask_logit;
+  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar;
+  const EgnnWorkspace* ws;
+  float* logits_out; float* score_out; int32_t* status;
+  int64_t n_nodes; int32_t n_atoms;
+};
+bool tc_node_supported(const b200md_egnn_config& cfg, int precision);
+int64_t tc_node_packed_floats(const b200md_egnn_config& cfg);
+int tc_node_pack_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, int layer, float* packed, cudaStream_t st);
+int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const float* packed, const NodeCall& call,
+                   int precision, cudaStream_t st);
 
 }  // namespace b200md

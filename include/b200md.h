@@ -47,6 +47,7 @@ typedef enum {
 #define B200MD_STATUS_MASK_REMAINS 16u      /* generators/langevin_generator.py:616-620 */
 #define B200MD_STATUS_BAD_LOGITS 32u        /* utils/d3pm_utils.py:143-145 */
 #define B200MD_STATUS_SIGMA_OUT_OF_RANGE 64u
+#define B200MD_STATUS_TC_RANGE 128u         /* an activation exceeded the fp16 range of B200MD_IMPL_TCGEN05_F16X3 */
 
 const char* b200md_error_string(int code);
 int b200md_abi_version(void);
@@ -269,6 +270,8 @@ int64_t b200md_egnn_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_sam
 #define B200MD_IMPL_AUTO 0
 #define B200MD_IMPL_FFMA 1    /* fp32 CUDA-core tiles */
 #define B200MD_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma tiles, fp32 accumulate in TMEM */
+#define B200MD_IMPL_TCGEN05_F16X3 3 /* 3xFP16 tcgen05.mma tiles (same 11-bit significands, half the operand bytes);
+                                      activations beyond the fp16 range raise B200MD_STATUS_TC_RANGE */
 
 /* The implementation B200MD_IMPL_AUTO resolves to for this configuration (B200MD_IMPL_FFMA or B200MD_IMPL_TCGEN05),
  * or a negative error when `impl` is not available for it. */

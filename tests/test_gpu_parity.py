@@ -314,13 +314,17 @@ PRODUCTION = dict(edges="radial_cutoff", radial_cutoff=7.5, n_layers=4, message_
                   coordinate_n_hidden_dimensions=4, coordinate_hidden_dimensions_size=256)
 
 
-@pytest.mark.parametrize("impl", [_cabi.IMPL_FFMA, _cabi.IMPL_TCGEN05], ids=["ffma", "tcgen05"])
+TC_IMPLS = [_cabi.IMPL_TCGEN05, _cabi.IMPL_TCGEN05_F16X3]
+TC_IDS = ["tf32x3", "f16x3"]
+
+
+@pytest.mark.parametrize("impl", [_cabi.IMPL_FFMA] + TC_IMPLS, ids=["ffma"] + TC_IDS)
 @pytest.mark.parametrize("num_atom_types,N,B,length", [(1, 64, 6, 10.86), (2, 64, 4, 11.084), (1, 216, 2, 16.29)])
 def test_egnn_forward_production_width_against_oracle(cuda_device, num_atom_types, N, B, length, impl):
     """Production widths of the reference's Si/SiGe configs (256 x 4 hidden layers, 4 E_GCL, rc = 7.5, mean agg),
     with the fp32 CUDA-core edge kernel and with the tcgen05 3xTF32 edge kernel."""
     net = run_against_oracle(cuda_device, dict(num_atom_types=num_atom_types, **PRODUCTION), N, B, length, impl)
-    assert ("tcgen05" in net.last_edge_kernel_name()) == (impl == _cabi.IMPL_TCGEN05)
+    assert ("tcgen05" in net.last_edge_kernel_name()) == (impl != _cabi.IMPL_FFMA)
 
 
 @pytest.mark.parametrize("hp", [
@@ -331,16 +335,47 @@ def test_egnn_forward_production_width_against_oracle(cuda_device, num_atom_type
          coordinate_n_hidden_dimensions=1, node_hidden_dimensions_size=32, n_layers=3, residual=False),
     dict(message_hidden_dimensions_size=256, coordinate_hidden_dimensions_size=64, message_n_hidden_dimensions=1,
          coordinate_n_hidden_dimensions=3, node_hidden_dimensions_size=128, n_layers=1, edges="fully_connected"),
-], ids=["96x160-norm-tanh-sum", "32-no-hidden-message", "256to64-fully-connected"])
-def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp):
-    """The tensor-core edge kernel over its whole supported envelope: any widths that are multiples of 32 (<= 256),
-    any number of hidden layers, normalize / tanh, sum or mean aggregation, both edge modes."""
+    dict(message_hidden_dimensions_size=128, coordinate_hidden_dimensions_size=192, message_n_hidden_dimensions=2,
+         coordinate_n_hidden_dimensions=2, node_hidden_dimensions_size=64, node_n_hidden_dimensions=3, n_layers=2,
+         normalize=True, message_agg="sum"),
+], ids=["96x160-norm-tanh-sum", "32-no-hidden-message", "256to64-fully-connected", "128x192x64"])
+@pytest.mark.parametrize("impl", TC_IMPLS, ids=TC_IDS)
+def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp, impl):
+    """The tensor-core kernels over their whole supported envelope: widths that are multiples of 32 (3xTF32) or 64
+    (3xFP16) up to 256, any number of hidden layers, normalize / tanh, sum or mean aggregation, both edge modes."""
     full = dict(num_atom_types=2, edges="radial_cutoff", radial_cutoff=3.1)
     full.update(hp)
     if full["edges"] == "fully_connected":
         full.pop("radial_cutoff")
-    net = run_against_oracle(cuda_device, full, 40, 5, 7.0, _cabi.IMPL_TCGEN05, seed=8)
+    widths = [full[k] for k in ("message_hidden_dimensions_size", "coordinate_hidden_dimensions_size")]
+    if impl == _cabi.IMPL_TCGEN05_F16X3 and any(w % 64 for w in widths):
+        with pytest.raises(_cabi.B200MDError):
+            run_against_oracle(cuda_device, full, 40, 5, 7.0, impl, seed=8)
+        return
+    net = run_against_oracle(cuda_device, full, 40, 5, 7.0, impl, seed=8)
     assert "tcgen05" in net.last_edge_kernel_name()
+
+
+def test_fp16_range_guard(cuda_device):
+    """3xFP16 kernels flag activations beyond the fp16 range instead of silently saturating."""
+    hp = dict(num_atom_types=1, edges="radial_cutoff", radial_cutoff=3.1, message_hidden_dimensions_size=64,
+              coordinate_hidden_dimensions_size=64, node_hidden_dimensions_size=64, n_layers=1)
+    torch.manual_seed(3)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
+    with torch.no_grad():
+        net.egnn.graph_layers[0].message_mlp[2].bias.fill_(1.0e6)  # pushes the message activations to ~1e6
+    net = net.to(cuda_device)
+    x = torch.rand(2, 24, 3)
+    a = torch.zeros(2, 24, dtype=torch.long)
+    lattice = torch.zeros(2, 6)
+    lattice[:, :3] = 7.0
+    sigma = torch.full((2, 1), 0.1)
+    net.kernel_impl = _cabi.IMPL_TCGEN05_F16X3
+    with pytest.raises(AssertionError, match="fp16 range"):
+        net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
+    net.kernel_impl = _cabi.IMPL_TCGEN05
+    out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)  # 3xTF32 has the fp32 range
+    assert bool(torch.isfinite(out.X).all())
 
 
 def test_tcgen05_unsupported_configuration_is_refused(cuda_device):
