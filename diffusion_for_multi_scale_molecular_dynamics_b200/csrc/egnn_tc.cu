@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_tc_kernel(const EdgeTcA
     if (lane == 0) pipe.run_mma(p, sched.n_iterations);
   } else {
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int hh = (warp - 2) >> 2;       // which half of a chunk's columns
+    const int hh = (warp - 2) >> 2;       // which quarter of a chunk's columns
     float vmax = 0.f;                     // largest activation handed to the tensor cores (fp16 range guard)
     const int row = q * 32 + lane;        // row of the tile = TMEM lane
     const uint32_t lane_taddr = pipe.tmem_base + ((uint32_t)(q * 32) << 16);

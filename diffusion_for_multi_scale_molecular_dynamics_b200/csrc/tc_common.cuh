@@ -28,7 +28,8 @@ constexpr int kRowBytes = 128;         // operand rows are one 128-byte swizzle 
 constexpr int kMaxN = 256;             // widest layer (UMMA N limit)
 constexpr int kAStages = 2;
 constexpr int kBStages = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;           // 4 per TMEM lane quarter: each owns a quarter of a chunk's columns
+constexpr int kEpiParts = kEpiWarps / 4;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kMaxGemms = 10;
 constexpr int kAPartBytes = kTileM * 128;            // one 128-byte-per-row operand of an A stage (16 KB)
@@ -41,7 +42,7 @@ enum Precision { kTf32x3 = 0, kF16x3 = 1 };
 template <int PREC>
 struct Mode {
   static constexpr int kChunk = (PREC == kF16x3) ? 64 : 32;   // K elements per chunk (128 bytes per row)
-  static constexpr int kVals = kChunk / 2;                    // activation values one epilogue thread handles per chunk
+  static constexpr int kVals = kChunk / kEpiParts;            // activation values one epilogue thread handles per chunk
 };
 // CTAs per thread-block cluster.  The CTAs of a cluster walk the same weight stream in lock-step: each one fetches
 // 1/kCluster of every weight part from L2 and multicasts it into the shared memory of all of them, which divides the
@@ -179,17 +180,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int N>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {
-  static_assert(N == 16 || N == 32, "16 or 32 accumulator columns per thread");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < N / 16; ++i) {
-    float t[16];
-    tmem_ld16(taddr + 16 * i, t);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[16 * i + j] = t[j];
-  }
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 
 // K-major, 128B-swizzled operand descriptor (cute::UMMA::SmemDescriptor): 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -391,21 +396,22 @@ struct Pipe {
     uint8_t* p1 = smem + L.a + sa * kAStageBytes;
     uint8_t* p2 = p1 + kAPartBytes;
     float vmax = 0.f;
+    // both modes: this thread owns 32 bytes of the 128-byte row = 16-byte units hh*2 and hh*2+1 of each part
     if (PREC == kTf32x3) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         float4 a1, a2;
         a1.x = tf32_rna(v[4 * j + 0]); a2.x = v[4 * j + 0] - a1.x;
         a1.y = tf32_rna(v[4 * j + 1]); a2.y = v[4 * j + 1] - a1.y;
         a1.z = tf32_rna(v[4 * j + 2]); a2.z = v[4 * j + 2] - a1.z;
         a1.w = tf32_rna(v[4 * j + 3]); a2.w = v[4 * j + 3] - a1.w;
-        const uint32_t off = sw128_offset(row, hh * 4 + j);
+        const uint32_t off = sw128_offset(row, hh * 2 + j);
         *reinterpret_cast<float4*>(p1 + off) = a1;
         *reinterpret_cast<float4*>(p2 + off) = a2;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {  // 8 values = 16 bytes of fp16 per iteration
+      for (int j = 0; j < 2; ++j) {  // 8 values = 16 bytes of fp16 per iteration
         uint32_t w1[4], w2[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -415,7 +421,7 @@ struct Pipe {
           const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&w1[i]));
           w2[i] = pack_f16x2(x0 - back.x, x1 - back.y);
         }
-        const uint32_t off = sw128_offset(row, hh * 4 + j);
+        const uint32_t off = sw128_offset(row, hh * 2 + j);
         *reinterpret_cast<uint4*>(p1 + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
         *reinterpret_cast<uint4*>(p2 + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
       }
