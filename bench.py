@@ -40,6 +40,9 @@ WORKLOADS = {
     "cfg1": ("Si 1x1x1 (8 atoms) EGNN, fully connected, PC Langevin", 8, 5.43, 1, dict(), 4096),
 }
 TOTAL_TIME_STEPS = 1000
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set full`
+# captures (profiles/ncu_full_*.txt; taken at 512 samples per launch, the weights and node features stay L2 resident)
+NCU_TRAFFIC_BYTES = {}
 PRODUCTION = dict(n_layers=4, message_n_hidden_dimensions=4, message_hidden_dimensions_size=256,
                   node_n_hidden_dimensions=4, node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4,
                   coordinate_hidden_dimensions_size=256)
@@ -278,11 +281,23 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
         avg_launch_s = edge_ms * 1e-3 / edge_launches
         flop_per_launch = samples * edges_per_structure * flops["f_edge"]
         achieved = flop_per_launch / avg_launch_s / 1e12
-        peak = 0.5 * peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": network.last_edge_kernel_name(), "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peaks["source"] + ": TF32 dense = 0.5 x measured sustained bf16 (kernel timed "
-                                   "inside a long step); fp32-exact 3xTF32 ceiling is one third of it",
+        kernel_name = network.last_edge_kernel_name()
+        # Denominator: the measured dense bf16/fp16 tensor throughput (sustained: the kernel is timed inside a long,
+        # power-capped step).  The 3xFP16 kernel issues three fp16 MMAs per algorithmic MAC (fp32-exact split), the
+        # 3xTF32 kernel three TF32 MMAs at half that rate; neither can exceed 1/3 (resp. 1/6) of the peak times
+        # 1.22 (the first message Linear is hoisted to the nodes: 1,180,160 of the 1,442,816 FLOP/edge run per edge).
+        peak = peaks["bf16_tflops_sustained"]
+        passes, rate = (3, 1.0) if "3xFP16" in kernel_name else ((3, 0.5) if "3xTF32" in kernel_name else (1, None))
+        executed_fraction = 1180160.0 / 1442816.0 if hp["message_hidden_dimensions_size"] == 256 else None
+        ceiling = None
+        if rate is not None and executed_fraction is not None:
+            ceiling = peak * rate / passes / executed_fraction
+        roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(args.kernels),
+                    "peak_source": peaks["source"] + ": dense bf16/fp16, sustained",
+                    "fp32_exact_passes": passes,
+                    "fp32_exact_ceiling_tflops": ceiling,
+                    "frac_of_fp32_exact_ceiling": (achieved / ceiling) if ceiling else None,
                     "algorithmic_flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                     "share_of_step": edge_ms / total_class_ms if total_class_ms else None,
                     "class_ms_per_step": {k: v[0] / profile_steps for k, v in classes.items()},
