@@ -36,6 +36,8 @@ WORKLOADS = {
              dict(), 4096),
     "cfg3": ("SiGe 2x2x2 (64 atoms) joint coordinate + atom-type diffusion, 1000 steps x1 corrector", 64, 11.084, 2,
              dict(one_atom_type_transition_per_step=True, atom_type_greedy_sampling=True), 4096),
+    "cfg4": ("Si 3x3x3 (216 atoms) repaint / constrained inpainting around a fixed cluster, 1000 steps x1 corrector",
+             216, 16.29, 1, dict(), 2048),
     "cfg5": ("synthetic Si 4x4x4 (512 atoms) EGNN, 1000 steps x1 corrector", 512, 21.72, 1, dict(), 1024),
     "cfg1": ("Si 1x1x1 (8 atoms) EGNN, fully connected, PC Langevin", 8, 5.43, 1, dict(), 4096),
 }
@@ -57,6 +59,21 @@ def network_hyper_parameters(workload: str) -> dict:
     else:
         hp.update(edges="radial_cutoff", radial_cutoff=7.5)
     return hp
+
+
+def diamond_cluster_constraint(cells: int, length: float, radius: float):
+    """Atoms of the perfect diamond lattice (cells^3 conventional cells) within `radius` of the cell centre: the fixed
+    cluster of BASELINE config 4, as a SamplingConstraint occupying the first atom slots."""
+    from diffusion_for_multi_scale_molecular_dynamics_b200.generators.sampling_constraint import SamplingConstraint
+    basis = torch.tensor([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [.25, .25, .25], [.25, .75, .75],
+                          [.75, .25, .75], [.75, .75, .25]])
+    grid = torch.stack(torch.meshgrid(*[torch.arange(cells)] * 3, indexing="ij"), dim=-1).reshape(-1, 1, 3)
+    relative = ((grid + basis.unsqueeze(0)) / cells).reshape(-1, 3)
+    distance = ((relative - 0.5) * length).norm(dim=1)
+    chosen = relative[distance <= radius].float().contiguous()
+    return SamplingConstraint(elements=["Si"], constrained_relative_coordinates=chosen,
+                              constrained_atom_types=torch.zeros(len(chosen), dtype=torch.long),
+                              constrained_indices=torch.arange(len(chosen)))
 
 
 def algorithmic_flops(hp: dict, n_atoms: int, edges_per_structure: float) -> dict:
@@ -217,11 +234,19 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     sampling = PredictorCorrectorSamplingParameters(
         number_of_samples=samples * world, number_of_atoms=atoms, num_atom_types=num_atom_types,
         number_of_corrector_steps=1, use_fixed_lattice_parameters=True, cell_dimensions=[length] * 3, **flags)
-    generator = LangevinGenerator(noise, sampling, network)
+    if workload == "cfg4":
+        from diffusion_for_multi_scale_molecular_dynamics_b200.generators.constrained_langevin_generator import \
+            ConstrainedLangevinGenerator
+        generator = ConstrainedLangevinGenerator(noise, sampling, network, diamond_cluster_constraint(3, length, 5.0))
+    else:
+        generator = LangevinGenerator(noise, sampling, network)
     generator.seed = 1234
     generator.sample_offset = rank * samples  # weak scaling: every rank owns `samples` structures
     K, W = args.steps, max(args.warmup, 3)
     assert W + K <= TOTAL_TIME_STEPS
+    if args.full_trajectory:
+        run_full_trajectory(args, generator, network, samples, world, rank, device, description)
+        return
 
     def barrier():
         if world > 1:
@@ -358,6 +383,34 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def run_full_trajectory(args, generator, network, samples, world, rank, device, description):
+    """Validation of the per-step extrapolation: time generator.sample() -- initialisation, all 1000 steps, final
+    device->host copy -- for `samples` structures per GPU and report structures/sec directly."""
+    import torch.distributed as dist
+    generator.sample(min(samples, 64), device)  # warm-up (weight packing, workspace)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    result = generator.sample(samples, device)
+    host = (result.X.cpu(), result.A.cpu())
+    stop.record()
+    torch.cuda.synchronize(device)
+    seconds = start.elapsed_time(stop) * 1e-3
+    if world > 1:
+        t = torch.tensor([seconds], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "structures/sec", "mode": "full trajectory (1000 PC steps, generator.sample)",
+                          "value": samples * world / seconds, "unit": "structures/s", "n_gpus": world,
+                          "seconds": seconds, "samples_per_gpu": samples, "workload": description,
+                          "edge_mlp": network.last_edge_kernel_name(),
+                          "all_unmasked": bool((host[1] != generator.masked_atom_type_index).all()),
+                          "x_in_unit_cell": bool(((host[0] >= 0) & (host[0] < 1)).all())}), flush=True)
+
+
 def measure_edges(network, composition, device) -> float:
     """Directed edges per structure of the current batch (one extra forward, outside the timed region)."""
     from diffusion_for_multi_scale_molecular_dynamics_b200.namespace import (CARTESIAN_FORCES, NOISE,
@@ -391,6 +444,8 @@ def main():
     parser.add_argument("--samples", type=int, default=None, help="samples per GPU (default: the workload's)")
     parser.add_argument("--cpu-samples", type=int, default=32, help="structures per CPU-baseline step")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--full-trajectory", action="store_true",
+                        help="time one complete generator.sample() of --samples structures instead of K steps")
     parser.add_argument("--kernels", choices=["auto", "ffma", "tf32x3", "f16x3"], default="auto",
                         help="edge/node MLP implementation (auto = what the library picks for the configuration)")
     args = parser.parse_args()
