@@ -43,8 +43,9 @@ WORKLOADS = {
 }
 TOTAL_TIME_STEPS = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set full`
-# captures (profiles/ncu_full_*.txt; taken at 512 samples per launch, the weights and node features stay L2 resident)
-NCU_TRAFFIC_BYTES = {}
+# captures (profiles/ncu_full_r01f.txt: egnn_edge_tc_kernel<3xFP16>, 4096 samples; the algorithmic minimum is
+# P + Q + xcur reads, agg read-modify-write and the edge list: about 0.86 GB)
+NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 874239488 + 254038784, ("cfg2", 4096, "f16x3"): 874239488 + 254038784}
 PRODUCTION = dict(n_layers=4, message_n_hidden_dimensions=4, message_hidden_dimensions_size=256,
                   node_n_hidden_dimensions=4, node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4,
                   coordinate_hidden_dimensions_size=256)
@@ -318,7 +319,7 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
         if rate is not None and executed_fraction is not None:
             ceiling = peak * rate / passes / executed_fraction
         roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(args.kernels),
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((workload, samples, args.kernels)),
                     "peak_source": peaks["source"] + ": dense bf16/fp16, sustained",
                     "fp32_exact_passes": passes,
                     "fp32_exact_ceiling_tflops": ceiling,

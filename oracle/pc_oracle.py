@@ -524,3 +524,24 @@ def pair_distance_histogram(x_rel: torch.Tensor, cell_lengths: torch.Tensor, r_m
         sel = dist[(dist > 0) & (dist <= r_max)]
         hist += torch.histc(sel, bins=bins, min=0.0, max=r_max)
     return hist
+
+
+def stillinger_weber_two_body_energy(x_rel: torch.Tensor, cell_lengths: torch.Tensor) -> torch.Tensor:
+    """Energy proxy per structure: the two-body term of the Stillinger-Weber Si potential
+    (data/stillinger_weber_coefficients/Si.sw: epsilon 2.1683 eV, sigma 2.0951 A, a 1.80, A 7.049556277, B 0.6022245584,
+    p 4, q 0) summed over all periodic pairs within a*sigma.  The reference evaluates energies through LAMMPS
+    (oracle/lammps.py:19-101), which is not available here; the pair term alone is a sufficient *statistic* to compare two
+    ensembles of sampled structures."""
+    eps, sig, a, A, B = 2.1683, 2.0951, 1.80, 7.049556277, 0.6022245584
+    cart = x_rel * cell_lengths[:, None, :]
+    images = relative_lattice_vectors().to(cart)
+    energy = torch.zeros(x_rel.shape[0], dtype=cart.dtype)
+    for img in range(27):
+        lat = images[img][None, :] * cell_lengths
+        diff = cart[:, :, None, :] - (cart[:, None, :, :] + lat[:, None, None, :])
+        r = torch.sqrt((diff**2).sum(-1)) / sig
+        inside = (r > 0.05) & (r < a - 1e-6)   # r > 0.05: skip self pairs / numerically coincident atoms
+        rr = torch.where(inside, r, torch.ones_like(r))
+        phi = A * eps * (B * rr**-4 - 1.0) * torch.exp(1.0 / (rr - a).clamp(max=-1e-6))
+        energy += 0.5 * torch.where(inside, phi, torch.zeros_like(phi)).sum(dim=(1, 2))
+    return energy

@@ -2,7 +2,7 @@
 # ncu evidence for the bench command (run via gpurun, 1 GPU).  $1 = tag for the output names.
 set -u
 TAG=${1:-r01}
-ARGS="--steps 2 --warmup 3 --samples 512 --no-cpu-baseline"
+ARGS="--steps 2 --warmup 3 --samples ${SAMPLES:-512} --no-cpu-baseline"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \

@@ -586,6 +586,13 @@ def test_trajectory_statistics_against_oracle(cuda_device):
     assert abs(h_gpu.sum() - h_ref.sum()) / h_ref.sum() < 0.05
     cdf_gpu, cdf_ref = torch.cumsum(h_gpu, 0) / h_gpu.sum(), torch.cumsum(h_ref, 0) / h_ref.sum()
     assert (cdf_gpu - cdf_ref).abs().max() < 0.04  # Kolmogorov-Smirnov distance between the two g(r) samples
+    # energy proxy (Stillinger-Weber pair term): Kolmogorov-Smirnov distance between the two ensembles
+    e_gpu = oracle.stillinger_weber_two_body_energy(sample.X.cpu(), lengths).clamp(max=1e4).sort().values
+    e_ref = oracle.stillinger_weber_two_body_energy(ref_x, lengths).clamp(max=1e4).sort().values
+    grid = torch.cat([e_gpu, e_ref]).sort().values
+    ks = (torch.searchsorted(e_gpu, grid, right=True) / len(e_gpu)
+          - torch.searchsorted(e_ref, grid, right=True) / len(e_ref)).abs().max()
+    assert ks < 1.63 * (2.0 / B) ** 0.5, f"energy-proxy KS distance {ks:.3f}"   # 1% two-sample KS critical value
     # atom-type composition: the same categorical marginals
     frac_gpu = torch.bincount(sample.A.cpu().flatten(), minlength=3).float() / (B * N)
     frac_ref = torch.bincount(ref_a.flatten(), minlength=3).float() / (B * N)
