@@ -136,6 +136,7 @@ SIGNATURES = {
     ),
     "b200md_wrapped_gaussian_score_f32": (c_int32, [_P, _P, c_int64, c_int32, _P, _P]),
     "b200md_wrapped_gaussian_score_f64": (c_int32, [_P, _P, c_int64, c_int32, _P, _P]),
+    "b200md_analytical_score_f32": (c_int32, [_P, _P, _P, c_float, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "b200md_segment_reduce": (c_int32, [_P, _P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "b200md_radius_graph_count": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "b200md_radius_graph_fill": (

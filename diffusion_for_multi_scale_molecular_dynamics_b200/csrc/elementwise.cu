@@ -352,56 +352,74 @@ __global__ void repaint_kernel(float* __restrict__ x, int64_t* __restrict__ a, c
 // Wrapped-Gaussian sigma-normalised score.   score/wrapped_gaussian_score.py:131-198,255-419
 // -------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void wrapped_gaussian_score_kernel(const T* __restrict__ u_in, const T* __restrict__ s_in,
-                                              int64_t n, int32_t kmax, T* __restrict__ out) {
+__device__ __forceinline__ T wrapped_gaussian_score_value(T u, T sigma, int32_t kmax) {
   const T pi = (T)3.14159265358979323846;
   // SIGMA_THRESHOLD = torch.Tensor([1/sqrt(2 pi)]) is a float32 tensor (:37); comparing an f64 sigma with
   // it promotes the float32 value, so the threshold is the float32-rounded number in both precisions.
   const T sigma_threshold = (T)(float)0.3989422804014327;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const T u = u_in[i];
-    const T sigma = s_in[i];
-    T result;
-    if (sigma <= sigma_threshold) {
-      // small sigma: sigma*S = (-u - sum_k k e_k / sum_k e_k) / sigma            (:301-367)
-      const bool small_u = u < (T)0.5;
-      const T s2 = sigma * sigma;
-      T num = 0, den = 0;
-      for (int k = -kmax; k <= kmax; ++k) {
-        const T kk = (T)k;
-        T arg;
-        if (small_u) arg = (T)(-0.5) * (kk * kk + (T)2.0 * u * kk) / s2;                       // (:271-273)
-        else arg = (T)(-0.5) * ((kk * kk - (T)1.0) + (T)2.0 * u * (kk + (T)1.0)) / s2;         // (:294-297)
-        const T e = exp(arg);
-        num += kk * e;
-        den += e;
-      }
-      result = (-u - num / den) / sigma;
-    } else {
-      // large sigma, Ewald form (:369-419)
-      T z2a = 0, z2b = 0, d1 = 0, d2 = 0;
-      for (int k = -kmax; k <= kmax; ++k) {
-        const T g = (T)k;
-        const T upk = u + g;
-        const T gu = u * g;
-        const T sg = sigma * g;
-        const T exp_upk = exp(-pi * upk * upk);
-        const T exp_sg = exp((T)(-2.0) * pi * pi * sg * sg);
-        const T exp_g = exp(-pi * g * g);
-        const T comb = sqrt((T)2.0 * pi) * sigma * exp_sg - exp_g;
-        T sn, cs;
-        sincos((T)2.0 * pi * gu, &sn, &cs);
-        z2a += exp_upk;
-        z2b += comb * cs;
-        d1 += upk * exp_upk;
-        d2 += g * comb * sn;
-      }
-      const T z2 = z2a + z2b;
-      const T deriv = (T)(-2.0) * pi * (d1 + d2);
-      result = sigma * deriv / z2;
+  if (sigma <= sigma_threshold) {
+    // small sigma: sigma*S = (-u - sum_k k e_k / sum_k e_k) / sigma            (:301-367)
+    const bool small_u = u < (T)0.5;
+    const T s2 = sigma * sigma;
+    T num = 0, den = 0;
+    for (int k = -kmax; k <= kmax; ++k) {
+      const T kk = (T)k;
+      T arg;
+      if (small_u) arg = (T)(-0.5) * (kk * kk + (T)2.0 * u * kk) / s2;                       // (:271-273)
+      else arg = (T)(-0.5) * ((kk * kk - (T)1.0) + (T)2.0 * u * (kk + (T)1.0)) / s2;         // (:294-297)
+      const T e = exp(arg);
+      num += kk * e;
+      den += e;
     }
-    out[i] = result;
+    return (-u - num / den) / sigma;
+  }
+  // large sigma, Ewald form (:369-419)
+  T z2a = 0, z2b = 0, d1 = 0, d2 = 0;
+  for (int k = -kmax; k <= kmax; ++k) {
+    const T g = (T)k;
+    const T upk = u + g;
+    const T gu = u * g;
+    const T sg = sigma * g;
+    const T exp_upk = exp(-pi * upk * upk);
+    const T exp_sg = exp((T)(-2.0) * pi * pi * sg * sg);
+    const T exp_g = exp(-pi * g * g);
+    const T comb = sqrt((T)2.0 * pi) * sigma * exp_sg - exp_g;
+    T sn, cs;
+    sincos((T)2.0 * pi * gu, &sn, &cs);
+    z2a += exp_upk;
+    z2b += comb * cs;
+    d1 += upk * exp_upk;
+    d2 += g * comb * sn;
+  }
+  const T z2 = z2a + z2b;
+  const T deriv = (T)(-2.0) * pi * (d1 + d2);
+  return sigma * deriv / z2;
+}
+
+template <typename T>
+__global__ void wrapped_gaussian_score_kernel(const T* __restrict__ u_in, const T* __restrict__ s_in,
+                                              int64_t n, int32_t kmax, T* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = wrapped_gaussian_score_value<T>(u_in[i], s_in[i], kmax);
+}
+
+// AnalyticalScoreNetwork without permutation symmetry (models/score_networks/analytical_score_network.py:134-298):
+//   u = wrap(x - x0);  sigma_eff = sqrt(sigma_d^2 + sigma_t^2);  out = sigma_t * (S(u, sigma_eff) / sigma_eff)
+__global__ void analytical_score_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                                        const float* __restrict__ sigma_t, float sigma_d_square,
+                                        int64_t n_samples, int32_t per_sample, int32_t kmax,
+                                        float* __restrict__ out) {
+  const int64_t total = n_samples * per_sample;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t smp = i / per_sample;
+    const int32_t k = (int32_t)(i - smp * per_sample);
+    const float st = sigma_t[smp];
+    const float u = wrap_unit(__fsub_rn(x[i], x0[k]));
+    const float se = sqrtf(__fadd_rn(sigma_d_square, __fmul_rn(st, st)));
+    const float s = wrapped_gaussian_score_value<float>(u, se, kmax);
+    out[i] = __fmul_rn(st, __fdiv_rn(s, se));
   }
 }
 
@@ -558,6 +576,20 @@ int b200md_wrapped_gaussian_score_f64(const double* u, const double* sigma, int6
   if (n < 0 || kmax < 0 || (n > 0 && (!u || !sigma || !out))) return B200MD_ERR_INVALID_ARGUMENT;
   if (n == 0) return B200MD_OK;
   { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); wrapped_gaussian_score_kernel<double><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(u, sigma, n, kmax, out); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_analytical_score_f32(const float* x, const float* x0, const float* sigma_t, float sigma_d,
+                                int64_t n_samples, int32_t n_atoms, int32_t spatial_dimension, int32_t kmax,
+                                float* out, b200md_stream_t stream) {
+  if (n_samples < 0 || n_atoms <= 0 || spatial_dimension <= 0 || kmax < 0 || !(sigma_d > 0.f) ||
+      (n_samples > 0 && (!x || !x0 || !sigma_t || !out)))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0) return B200MD_OK;
+  const int32_t per_sample = n_atoms * spatial_dimension;
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); analytical_score_kernel<<<grid_for(n_samples * per_sample, 256), 256, 0, as_stream(stream)>>>(
+        x, x0, sigma_t, sigma_d * sigma_d, n_samples, per_sample, kmax, out); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }

@@ -1,18 +1,20 @@
 """Registry of score networks on the sm_100a sampling path (reference: models/score_networks/score_network_factory.py).
 
-Only the EGNN architecture is implemented natively; the reference's other architectures (mlp, mace, diffusion_mace,
-analytical, ...) are outside the accelerated path and raise ``NotImplementedError`` here.
+The EGNN and the (non-symmetrised) analytical score network are implemented natively; the reference's other
+architectures (mlp, mace, diffusion_mace, ...) are outside the accelerated path and raise ``NotImplementedError``.
 """
 import dataclasses
 from typing import Any, AnyStr, Dict
 
+from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.analytical_score_network import (
+    AnalyticalScoreNetwork, AnalyticalScoreNetworkParameters)
 from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.egnn_score_network import (
     EGNNScoreNetwork, EGNNScoreNetworkParameters)
 from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.score_network import (
     ScoreNetwork, ScoreNetworkParameters)
 
-SCORE_NETWORKS_BY_ARCH = dict(egnn=EGNNScoreNetwork)
-SCORE_NETWORK_PARAMETERS_BY_ARCH = dict(egnn=EGNNScoreNetworkParameters)
+SCORE_NETWORKS_BY_ARCH = dict(egnn=EGNNScoreNetwork, analytical=AnalyticalScoreNetwork)
+SCORE_NETWORK_PARAMETERS_BY_ARCH = dict(egnn=EGNNScoreNetworkParameters, analytical=AnalyticalScoreNetworkParameters)
 
 
 def create_score_network(score_network_parameters: ScoreNetworkParameters) -> ScoreNetwork:

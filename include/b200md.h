@@ -165,6 +165,14 @@ int b200md_wrapped_gaussian_score_f32(const float* u, const float* sigma, int64_
 int b200md_wrapped_gaussian_score_f64(const double* u, const double* sigma, int64_t n,
                                       int32_t kmax, double* out, b200md_stream_t stream);
 
+/* AnalyticalScoreNetwork._forward_unchecked without permutation symmetry
+ * (models/score_networks/analytical_score_network.py:134-298): the exact sigma-normalised score of isotropic Gaussian
+ * displacements of width sigma_d around equilibrium positions x0 [N,d], noised to sigma_t [B]:
+ *   u = wrap(x - x0), sigma_eff = sqrt(sigma_d^2 + sigma_t^2), out = sigma_t * S_wrapped(u, sigma_eff) / sigma_eff.   */
+int b200md_analytical_score_f32(const float* x, const float* x0, const float* sigma_t, float sigma_d,
+                                int64_t n_samples, int32_t n_atoms, int32_t spatial_dimension, int32_t kmax,
+                                float* out, b200md_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * unsorted_segment_sum / unsorted_segment_mean (models/egnn_utils.py:11-70).
  * data [E,F] f32, segment_ids [E] int64 in [0,num_segments); out [num_segments,F].

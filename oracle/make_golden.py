@@ -29,6 +29,8 @@ from diffusion_for_multi_scale_molecular_dynamics.generators.sampling_constraint
 from diffusion_for_multi_scale_molecular_dynamics.models.egnn_utils import (get_edges_with_radial_cutoff,  # noqa: E402
                                                                              unsorted_segment_mean,
                                                                              unsorted_segment_sum)
+from diffusion_for_multi_scale_molecular_dynamics.models.score_networks.analytical_score_network import (  # noqa: E402
+    AnalyticalScoreNetwork, AnalyticalScoreNetworkParameters)
 from diffusion_for_multi_scale_molecular_dynamics.models.score_networks.egnn_score_network import (  # noqa: E402
     EGNNScoreNetwork, EGNNScoreNetworkParameters)
 from diffusion_for_multi_scale_molecular_dynamics.namespace import (AXL, CARTESIAN_FORCES, NOISE,  # noqa: E402
@@ -278,6 +280,39 @@ def golden_trajectories():
     save("trajectories", **out)
 
 
+DIAMOND = [[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [.25, .25, .25], [.25, .75, .75], [.75, .25, .75],
+           [.75, .75, .25]]
+
+
+def golden_analytical():
+    """AnalyticalScoreNetwork forward and a whole PC trajectory driven by it (Si 1x1x1 diamond, sigma_d = 0.01)."""
+    out = {}
+    params = AnalyticalScoreNetworkParameters(number_of_atoms=8, num_atom_types=1, kmax=4,
+                                              equilibrium_relative_coordinates=DIAMOND, sigma_d=0.01)
+    net = AnalyticalScoreNetwork(params)
+    torch.manual_seed(21)
+    B = 6
+    x = torch.rand(B, 8, 3)
+    sigma = torch.tensor([0.005, 0.02, 0.1, 0.3, 0.45, 0.5]).reshape(B, 1)
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = 5.43
+    batch = {NOISY_AXL_COMPOSITION: AXL(A=torch.ones(B, 8, dtype=torch.long), X=x, L=lattice), TIME: torch.rand(B, 1),
+             NOISE: sigma, CARTESIAN_FORCES: torch.zeros_like(x)}
+    result = net(batch, conditional=False)
+    out.update(x=x, sigma=sigma, score=result.X, logits=result.A, x0=torch.tensor(DIAMOND))
+    T, n_corr = 25, 1
+    sampling = PredictorCorrectorSamplingParameters(number_of_samples=B, number_of_atoms=8, num_atom_types=1,
+                                                    number_of_corrector_steps=n_corr, use_fixed_lattice_parameters=True,
+                                                    cell_dimensions=[5.43] * 3)
+    gen = LangevinGenerator(NoiseParameters(total_time_steps=T), sampling, net)
+    x_start = torch.rand(B, 8, 3)
+    a_start = torch.ones(B, 8, dtype=torch.long)
+    with torch.no_grad(), TapedHooks(gen, NoiseTape(seed=31)):
+        final = gen.sample_from_noisy_composition(AXL(A=a_start.clone(), X=x_start.clone(), L=lattice.clone()), T, 0)
+    out.update(traj_x0=x_start, traj_final_x=final.X, traj_final_a=final.A, T=T)
+    save("analytical", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     golden_noise_tables()
@@ -287,3 +322,4 @@ if __name__ == "__main__":
     golden_egnn()
     golden_atom_types()
     golden_trajectories()
+    golden_analytical()

@@ -375,6 +375,15 @@ def wrapped_gaussian_score(u: torch.Tensor, sigma: torch.Tensor, kmax: int) -> t
     return out.reshape(u.shape)
 
 
+def analytical_score(x: torch.Tensor, x0: torch.Tensor, sigma_t: torch.Tensor, sigma_d: float, kmax: int) -> torch.Tensor:
+    """AnalyticalScoreNetwork without permutation symmetry (models/score_networks/analytical_score_network.py:134-298):
+    sigma_t * S_wrapped(wrap(x - x0), sigma_eff) / sigma_eff with sigma_eff = sqrt(sigma_d^2 + sigma_t^2)."""
+    sig = sigma_t.reshape(-1, 1, 1).to(x).expand_as(x)
+    effective = torch.sqrt(sigma_d**2 + sig**2)
+    u = wrap_to_unit_cell(x - x0.unsqueeze(0))
+    return sig * (wrapped_gaussian_score(u, effective, kmax) / effective)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Noise tape: deterministic noise shared by the reference, the oracle and the CUDA path in parity tests
 # ---------------------------------------------------------------------------------------------------------

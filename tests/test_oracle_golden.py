@@ -128,3 +128,33 @@ def test_trajectory(name):
     delta = (x - g["final_x"]).abs()
     delta = torch.minimum(delta, 1.0 - delta)
     assert delta.max() < 2e-5, delta.max()
+
+
+def test_analytical_score_network():
+    g = load_golden("analytical")
+    score = oracle.analytical_score(g["x"], g["x0"], g["sigma"], 0.01, 4)
+    torch.testing.assert_close(score, g["score"], rtol=2e-5, atol=2e-5)
+
+
+def test_analytical_trajectory():
+    """A whole trajectory driven by the analytical score: contractive dynamics, so coordinates agree tightly."""
+    g = load_golden("analytical")
+    T = int(g["T"])
+    tables = oracle.noise_tables(T, 2)
+    B = g["traj_x0"].shape[0]
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = 5.43
+
+    def score_fn(a, x, lat, sigma):
+        logits = torch.zeros(B, 8, 2)
+        logits[..., -1] = -torch.inf
+        return logits, oracle.analytical_score(x, g["x0"], torch.full((B,), sigma), 0.01, 4)
+
+    a, x, _ = oracle.pc_sample(score_fn, tables, torch.ones(B, 8, dtype=torch.long), g["traj_x0"], lattice,
+                               oracle.NoiseTape(31))
+    assert torch.equal(a, g["traj_final_a"])
+    delta = (x - g["traj_final_x"]).abs()
+    assert torch.minimum(delta, 1.0 - delta).max() < 2e-5
+    # the samples sit within a few sigma_d of the equilibrium positions
+    d0 = (x - g["x0"]).abs()
+    assert torch.minimum(d0, 1.0 - d0).max() < 0.08
