@@ -313,6 +313,19 @@ def golden_analytical():
     save("analytical", **out)
 
 
+def golden_checkpoint():
+    """A checkpoint shaped like the reference's Lightning checkpoints: ``state_dict`` keys under ``axl_network.`` and the
+    reference's own parameter dataclass pickled (by class name) inside ``hyper_parameters``."""
+    net = make_network("radial_sige", seed=500)
+    state = {"axl_network." + k: v for k, v in net.state_dict().items()}
+    state["loss_calculator.weights"] = torch.ones(3)  # something that is not part of the score network
+    hyper = {"hyper_params": {"score_network_parameters": EGNNScoreNetworkParameters(**EGNN_VARIANTS["radial_sige"]),
+                              "kmax_target_score": 4}}
+    path = os.path.join(OUT, "lightning_like_checkpoint.ckpt")
+    torch.save({"state_dict": state, "hyper_parameters": hyper, "epoch": 3, "pytorch-lightning_version": "2.2.0"}, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KB)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     golden_noise_tables()
@@ -323,3 +336,4 @@ if __name__ == "__main__":
     golden_atom_types()
     golden_trajectories()
     golden_analytical()
+    golden_checkpoint()
