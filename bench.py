@@ -230,7 +230,7 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     torch.manual_seed(1234)
     network = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp)).to(device)
     network.kernel_impl = {"auto": _cabi.IMPL_AUTO, "ffma": _cabi.IMPL_FFMA, "tf32x3": _cabi.IMPL_TCGEN05,
-                           "f16x3": _cabi.IMPL_TCGEN05_F16X3}[args.kernels]
+                           "f16x3": _cabi.IMPL_TCGEN05_F16X3, "f16x3ts": _cabi.IMPL_TCGEN05_F16X3_TS}[args.kernels]
     noise = NoiseParameters(total_time_steps=TOTAL_TIME_STEPS)
     sampling = PredictorCorrectorSamplingParameters(
         number_of_samples=samples * world, number_of_atoms=atoms, num_atom_types=num_atom_types,
@@ -447,7 +447,7 @@ def main():
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--full-trajectory", action="store_true",
                         help="time one complete generator.sample() of --samples structures instead of K steps")
-    parser.add_argument("--kernels", choices=["auto", "ffma", "tf32x3", "f16x3"], default="auto",
+    parser.add_argument("--kernels", choices=["auto", "ffma", "tf32x3", "f16x3", "f16x3ts"], default="auto",
                         help="edge/node MLP implementation (auto = what the library picks for the configuration)")
     args = parser.parse_args()
 

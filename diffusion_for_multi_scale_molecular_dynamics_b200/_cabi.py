@@ -49,7 +49,7 @@ DRAW_INIT_UNIFORM, DRAW_REPAINT_NORMAL, DRAW_REPAINT_UNIFORM, DRAW_REPAINT_INIT 
 
 ATOM_GREEDY, ATOM_ONE_TRANSITION, ATOM_LAST_STEP = 1, 2, 4
 GRAPH_UNIQUE_PAIRS, GRAPH_PER_IMAGE = 0, 1
-IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05, IMPL_TCGEN05_F16X3 = 0, 1, 2, 3
+IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05, IMPL_TCGEN05_F16X3, IMPL_TCGEN05_F16X3_TS = 0, 1, 2, 3, 4
 
 EGNN_RESIDUAL, EGNN_ATTENTION, EGNN_NORMALIZE, EGNN_TANH = 1, 2, 4, 8
 EGNN_COORDS_MEAN, EGNN_MESSAGE_MEAN, EGNN_RADIAL_CUTOFF, EGNN_KEEP_DUPLICATES = 16, 32, 64, 128

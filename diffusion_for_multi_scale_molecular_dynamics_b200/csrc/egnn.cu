@@ -544,16 +544,19 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
     attrs_set = true;
   }
   // B200MD_IMPL_TCGEN05: 3xTF32 tensor-core kernels (any widths that are multiples of 32); B200MD_IMPL_TCGEN05_F16X3:
-  // 3xFP16 (multiples of 64); AUTO prefers F16X3, then TF32, then the CUDA-core kernels.
+  // 3xFP16 (multiples of 64), A operand through shared memory; B200MD_IMPL_TCGEN05_F16X3_TS: 3xFP16 with the edge
+  // kernel's A operand in tensor memory; AUTO prefers F16X3_TS, then TF32, then the CUDA-core kernels.
   bool use_tc = false;
-  int precision = 0;
-  if (impl == B200MD_IMPL_TCGEN05 || impl == B200MD_IMPL_TCGEN05_F16X3) {
-    precision = (impl == B200MD_IMPL_TCGEN05_F16X3) ? 1 : 0;
-    if (!tc_edge_supported(cfg, precision)) return B200MD_ERR_UNSUPPORTED;
+  int precision = 0;        // of the node kernel
+  int edge_precision = 0;   // of the edge kernel
+  if (impl == B200MD_IMPL_TCGEN05 || impl == B200MD_IMPL_TCGEN05_F16X3 || impl == B200MD_IMPL_TCGEN05_F16X3_TS) {
+    precision = (impl == B200MD_IMPL_TCGEN05) ? 0 : 1;
+    edge_precision = (impl == B200MD_IMPL_TCGEN05) ? 0 : (impl == B200MD_IMPL_TCGEN05_F16X3 ? 1 : 2);
+    if (!tc_edge_supported(cfg, edge_precision)) return B200MD_ERR_UNSUPPORTED;
     use_tc = true;
   } else if (impl == B200MD_IMPL_AUTO) {
-    if (tc_edge_supported(cfg, 1) && tc_node_supported(cfg, 1)) { use_tc = true; precision = 1; }
-    else if (tc_edge_supported(cfg, 0)) { use_tc = true; precision = 0; }
+    if (tc_edge_supported(cfg, 2) && tc_node_supported(cfg, 1)) { use_tc = true; precision = 1; edge_precision = 2; }
+    else if (tc_edge_supported(cfg, 0)) { use_tc = true; precision = 0; edge_precision = 0; }
   } else if (impl != B200MD_IMPL_FFMA) {
     return B200MD_ERR_INVALID_ARGUMENT;
   }
@@ -598,7 +601,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
 
   for (int l = 0; l < cfg.n_layers; ++l) {
     if (use_tc) {
-      rc = tc_launch_edge_layer(cfg, lay, l, packed, ws, status, precision, st);
+      rc = tc_launch_edge_layer(cfg, lay, l, packed, ws, status, edge_precision, st);
       if (rc != B200MD_OK) return rc;
     } else {
       EdgeArgs ea{};
@@ -745,10 +748,11 @@ int b200md_egnn_resolve_impl(const b200md_egnn_config* cfg, int32_t impl) {
   int rc = build_layout(*cfg, lay);
   if (rc != B200MD_OK) return rc;
   if (impl == B200MD_IMPL_FFMA) return B200MD_IMPL_FFMA;
-  if (impl == B200MD_IMPL_TCGEN05 || impl == B200MD_IMPL_TCGEN05_F16X3)
-    return tc_edge_supported(*cfg, impl == B200MD_IMPL_TCGEN05_F16X3 ? 1 : 0) ? impl : B200MD_ERR_UNSUPPORTED;
+  if (impl == B200MD_IMPL_TCGEN05 || impl == B200MD_IMPL_TCGEN05_F16X3 || impl == B200MD_IMPL_TCGEN05_F16X3_TS)
+    return tc_edge_supported(*cfg, impl == B200MD_IMPL_TCGEN05 ? 0 : (impl == B200MD_IMPL_TCGEN05_F16X3 ? 1 : 2))
+               ? impl : B200MD_ERR_UNSUPPORTED;
   if (impl == B200MD_IMPL_AUTO) {
-    if (tc_edge_supported(*cfg, 1) && tc_node_supported(*cfg, 1)) return B200MD_IMPL_TCGEN05_F16X3;
+    if (tc_edge_supported(*cfg, 2) && tc_node_supported(*cfg, 1)) return B200MD_IMPL_TCGEN05_F16X3_TS;
     return tc_edge_supported(*cfg, 0) ? B200MD_IMPL_TCGEN05 : B200MD_IMPL_FFMA;
   }
   return B200MD_ERR_INVALID_ARGUMENT;

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
   if (warp == 0) {
     if (lane == 0 && p.n_gemms > 0) pipe.run_producer(p, sched.n_iterations);
   } else if (warp == 1) {
-    if (lane == 0 && p.n_gemms > 0) pipe.run_mma(p, sched.n_iterations);
+    if (p.n_gemms > 0) pipe.run_mma(p, sched.n_iterations);
   } else {
     const int q = warp & 3;
     const int hh = (warp - 2) >> 2;

@@ -38,7 +38,7 @@ constexpr int kBStageBytes = kMaxN * 128;            // one weight part of a K c
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 24;            // turns a protocol deadlock into a trap instead of a hang
 
-enum Precision { kTf32x3 = 0, kF16x3 = 1 };
+enum Precision { kTf32x3 = 0, kF16x3 = 1, kF16x3Ts = 2 };   // kF16x3Ts: edge kernel only, A operand in TMEM (egnn_tc.cu)
 template <int PREC>
 struct Mode {
   static constexpr int kChunk = (PREC == kF16x3) ? 64 : 32;   // K elements per chunk (128 bytes per row)
@@ -144,6 +144,22 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// The same descriptor as two words: the high word is a constant, the low word advances by 1 per 16 bytes of K offset
+// inside the swizzle atom (shared-memory addresses are < 2^18, so the 14-bit address field never carries).
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+// One lane of the (converged) warp.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T, issued by one thread for the CTA.
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -171,6 +187,35 @@ template <int PREC>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   if (PREC == kF16x3) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
   else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+// Same with both operand descriptors given by their low words (desc_lo_sw128); the high word is a constant.
+template <int PREC>
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_desc_lo, uint32_t b_desc_lo, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (PREC == kF16x3)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 ad, bd;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 ad, {%1, %5};\n"
+        "mov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_desc_lo), "r"(b_desc_lo), "r"(idesc), "r"(accumulate), "n"(kDescHiSw128)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 ad, bd;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 ad, {%1, %5};\n"
+        "mov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_desc_lo), "r"(b_desc_lo), "r"(idesc), "r"(accumulate), "n"(kDescHiSw128)
+        : "memory");
 }
 // Arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -350,44 +395,55 @@ struct Pipe {
     }
   }
 
-  // ===== MMA issuer: one thread =====
+  // ===== MMA issuer: the whole warp walks the loop (converged), one elected lane issues =====
+  // With a single thread inside the loop every operand sits in a vector register and the compiler wraps each
+  // tcgen05.mma in an ELECT / R2UR / branch "waterfall" (~40 instructions per MMA): the issuing thread, not the tensor
+  // pipe, then paces the kernel.  Converged, all addresses and descriptors live in uniform registers.
   __device__ void run_mma(const Program& p, int n_iterations) const {
     const PipeSmem L = pipe_smem();
     const uint16_t all_ctas = (uint16_t)((1u << kCluster) - 1u);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const bool leader = elect_one();
     uint32_t mca = 0, cb = 0, mgc = 0;
     for (int it = 0; it < n_iterations; ++it) {
       for (int g = 0; g < p.n_gemms; ++g, ++mgc) {
         const int nk = p.gK[g] / Mode<PREC>::kChunk;
         const uint32_t idesc = make_idesc(p.gN[g], PREC == kF16x3 ? 0u : 2u);
-        const uint32_t d_tmem = tmem_base + (mgc & 1u) * kMaxN;
+        const uint32_t d_tmem = tmem + (mgc & 1u) * kMaxN;
         for (int c = 0; c < nk; ++c, ++mca) {
           const uint32_t sa = mca % kAStages;
           mbar_wait(a_full(sa), (mca / kAStages) & 1u);
-          const uint32_t a1 = s_base + L.a + sa * kAStageBytes, a2 = a1 + kAPartBytes;
+          const uint32_t a1 = desc_lo_sw128(s_base + L.a + sa * kAStageBytes), a2 = desc_lo_sw128(s_base + L.a + sa * kAStageBytes + kAPartBytes);
           uint32_t sb = cb % kBStages;
           mbar_wait(b_full(sb), (cb / kBStages) & 1u);
           tc_fence_after();
-          uint32_t b_addr = s_base + L.b + sb * kBStageBytes;
+          uint32_t bd = desc_lo_sw128(s_base + L.b + sb * kBStageBytes);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 K-steps of 32 bytes: 8 tf32 or 16 fp16 elements
-            const uint64_t bd = make_desc_sw128(b_addr + k * 32);
-            umma<PREC>(d_tmem, make_desc_sw128(a1 + k * 32), bd, idesc, (c | k) != 0);  // A_1 B_1
-            umma<PREC>(d_tmem, make_desc_sw128(a2 + k * 32), bd, idesc, 1u);            // A_2 B_1
+            for (int k = 0; k < 4; ++k) {  // 4 K-steps of 32 bytes: 8 tf32 or 16 fp16 elements
+              umma_lo<PREC>(d_tmem, a1 + 2 * k, bd + 2 * k, idesc, (c | k) != 0);  // A_1 B_1
+              umma_lo<PREC>(d_tmem, a2 + 2 * k, bd + 2 * k, idesc, 1u);            // A_2 B_1
+            }
+            if (kCluster > 1) umma_commit_multicast(b_empty(sb), all_ctas); else umma_commit(b_empty(sb));
           }
-          if (kCluster > 1) umma_commit_multicast(b_empty(sb), all_ctas); else umma_commit(b_empty(sb));
+          __syncwarp();
           ++cb;
           sb = cb % kBStages;
           mbar_wait(b_full(sb), (cb / kBStages) & 1u);
           tc_fence_after();
-          b_addr = s_base + L.b + sb * kBStageBytes;
+          bd = desc_lo_sw128(s_base + L.b + sb * kBStageBytes);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // A_1 B_2
-            umma<PREC>(d_tmem, make_desc_sw128(a1 + k * 32), make_desc_sw128(b_addr + k * 32), idesc, 1u);
-          if (kCluster > 1) umma_commit_multicast(b_empty(sb), all_ctas); else umma_commit(b_empty(sb));
+            for (int k = 0; k < 4; ++k)  // A_1 B_2
+              umma_lo<PREC>(d_tmem, a1 + 2 * k, bd + 2 * k, idesc, 1u);
+            if (kCluster > 1) umma_commit_multicast(b_empty(sb), all_ctas); else umma_commit(b_empty(sb));
+            umma_commit(a_empty(sa));
+          }
+          __syncwarp();
           ++cb;
-          umma_commit(a_empty(sa));
         }
-        umma_commit(acc_full(mgc & 1u));
+        if (leader) umma_commit(acc_full(mgc & 1u));
+        __syncwarp();
       }
     }
   }

@@ -280,6 +280,8 @@ int64_t b200md_egnn_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_sam
 #define B200MD_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma tiles, fp32 accumulate in TMEM */
 #define B200MD_IMPL_TCGEN05_F16X3 3 /* 3xFP16 tcgen05.mma tiles (same 11-bit significands, half the operand bytes);
                                       activations beyond the fp16 range raise B200MD_STATUS_TC_RANGE */
+#define B200MD_IMPL_TCGEN05_F16X3_TS 4 /* 3xFP16 with the edge kernel's A operand in tensor memory: accumulators are
+                                         converted in place into the next layer's operand (no shared-memory round trip) */
 
 /* The implementation B200MD_IMPL_AUTO resolves to for this configuration (B200MD_IMPL_FFMA or B200MD_IMPL_TCGEN05),
  * or a negative error when `impl` is not available for it. */

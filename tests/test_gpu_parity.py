@@ -314,8 +314,9 @@ PRODUCTION = dict(edges="radial_cutoff", radial_cutoff=7.5, n_layers=4, message_
                   coordinate_n_hidden_dimensions=4, coordinate_hidden_dimensions_size=256)
 
 
-TC_IMPLS = [_cabi.IMPL_TCGEN05, _cabi.IMPL_TCGEN05_F16X3]
-TC_IDS = ["tf32x3", "f16x3"]
+TC_IMPLS = [_cabi.IMPL_TCGEN05, _cabi.IMPL_TCGEN05_F16X3, _cabi.IMPL_TCGEN05_F16X3_TS]
+TC_IDS = ["tf32x3", "f16x3", "f16x3ts"]
+F16_IMPLS = (_cabi.IMPL_TCGEN05_F16X3, _cabi.IMPL_TCGEN05_F16X3_TS)
 
 
 @pytest.mark.parametrize("impl", [_cabi.IMPL_FFMA] + TC_IMPLS, ids=["ffma"] + TC_IDS)
@@ -348,7 +349,7 @@ def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp, impl):
     if full["edges"] == "fully_connected":
         full.pop("radial_cutoff")
     widths = [full[k] for k in ("message_hidden_dimensions_size", "coordinate_hidden_dimensions_size")]
-    if impl == _cabi.IMPL_TCGEN05_F16X3 and any(w % 64 for w in widths):
+    if impl in F16_IMPLS and any(w % 64 for w in widths):
         with pytest.raises(_cabi.B200MDError):
             run_against_oracle(cuda_device, full, 40, 5, 7.0, impl, seed=8)
         return
@@ -356,7 +357,8 @@ def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp, impl):
     assert "tcgen05" in net.last_edge_kernel_name()
 
 
-def test_fp16_range_guard(cuda_device):
+@pytest.mark.parametrize("impl", [_cabi.IMPL_TCGEN05_F16X3, _cabi.IMPL_TCGEN05_F16X3_TS], ids=["f16x3", "f16x3ts"])
+def test_fp16_range_guard(cuda_device, impl):
     """3xFP16 kernels flag activations beyond the fp16 range instead of silently saturating."""
     hp = dict(num_atom_types=1, edges="radial_cutoff", radial_cutoff=3.1, message_hidden_dimensions_size=64,
               coordinate_hidden_dimensions_size=64, node_hidden_dimensions_size=64, n_layers=1)
@@ -370,7 +372,7 @@ def test_fp16_range_guard(cuda_device):
     lattice = torch.zeros(2, 6)
     lattice[:, :3] = 7.0
     sigma = torch.full((2, 1), 0.1)
-    net.kernel_impl = _cabi.IMPL_TCGEN05_F16X3
+    net.kernel_impl = impl
     with pytest.raises(AssertionError, match="fp16 range"):
         net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
     net.kernel_impl = _cabi.IMPL_TCGEN05
