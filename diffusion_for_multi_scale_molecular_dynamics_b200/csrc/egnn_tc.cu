@@ -221,7 +221,7 @@ __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
   L.wr = o; o += kMaxN * 4;
   L.wlast = o; o += kMaxN * 4;
-  L.dot = o; o += kTileM * 4;
+  L.dot = o; o += 2 * 4 * kTileM * 4;   // [tile parity][K step warp][row]
   L.total = o;
   return L;
 }
@@ -257,6 +257,18 @@ __device__ __forceinline__ uint32_t pack_f16x2_inf(float lo_elem, float hi_elem)
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
+
+// shared-memory load by window address (keeps the access an LDS: pointers derived from the aligned dynamic-smem base
+// lose their address space and become generic loads)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct TsPipe {
   uint32_t s_base, bar0, tmem_base;
@@ -383,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_ts_kernel(const EdgeTcA
     const int hh = (warp - 2) >> 2;       // K step of a chunk (16 columns) this warp converts
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = pipe.tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t sa_bias = pipe.s_base + L.bias, sa_wr = pipe.s_base + L.wr, sa_wlast = pipe.s_base + L.wlast;
     uint32_t ca = 0, gc = 0;
     bool poisoned = false;
 
@@ -404,66 +417,108 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_ts_kernel(const EdgeTcA
       ++ca;
     };
 
-    for (int it = 0; it < n_iterations; ++it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const int e = tile * kTileM + row;
-      const bool valid = e < E;
-      const int src = valid ? a.edge_src[e] : -1;
-      const int dst = valid ? a.edge_dst[e] : -1;
-      const int src_prev = __shfl_up_sync(0xffffffffu, src, 1);
-      const int src_next = __shfl_down_sync(0xffffffffu, src, 1);
-      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || src != src_prev);
-      const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-      const bool is_tail = (lane == 31) || (src != src_next);
-      float radial = 0.f;
-      if (valid)
+    // per-tile state of this thread's edge (row of the tile)
+    struct Edge {
+      int src, dst, seg_start;
+      bool valid, is_tail;
+      float radial;
+    };
+    auto load_edge = [&](int it) {
+      Edge ed;
+      const int e = ((int)blockIdx.x + it * (int)gridDim.x) * kTileM + row;
+      ed.valid = e < E;
+      ed.src = ed.valid ? a.edge_src[e] : -1;
+      ed.dst = ed.valid ? a.edge_dst[e] : -1;
+      // segments of equal source index inside this warp's 32 rows (edges are sorted by source)
+      const int src_prev = __shfl_up_sync(0xffffffffu, ed.src, 1);
+      const int src_next = __shfl_down_sync(0xffffffffu, ed.src, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || ed.src != src_prev);
+      ed.seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+      ed.is_tail = (lane == 31) || (ed.src != src_next);
+      ed.radial = 0.f;   // coord2radial (models/egnn.py:230-238)
+      if (ed.valid)
         for (int d = 0; d < a.D; ++d) {
-          const float df = a.xcur[(int64_t)src * a.D + d] - a.xcur[(int64_t)dst * a.D + d];
-          radial += df * df;
+          const float df = a.xcur[(int64_t)ed.src * a.D + d] - a.xcur[(int64_t)ed.dst * a.D + d];
+          ed.radial += df * df;
         }
-      if (hh == 0) s_dot[row] = 0.f;
-
-      // ---- first activation: silu(P[src] + Q[dst] + radial * w_r) -> A operand of GEMM gc ----
-      {
-        const uint32_t a_col = ((gc & 1u) ^ 1u) * kMaxN;
-        const int nk0 = M / 64;
-        for (int c = 0; c < nk0; ++c) {
-          const int col0 = c * 64 + hh * 16;
-          float v[16];
-          if (valid) {
-            const float4* p4 = reinterpret_cast<const float4*>(a.P + (int64_t)src * M + col0);
-            const float4* q4 = reinterpret_cast<const float4*>(a.Q + (int64_t)dst * M + col0);
+      return ed;
+    };
+    // 16 columns at once: inclusive segmented scans over the warp's rows (interleaved, so the shuffle latencies
+    // overlap), then one vector reduction per segment tail:  target[src, col0 .. col0 + 16) += sum over the segment
+    auto segment_add16 = [&](const Edge& ed, const float (&v)[16], float* target_row) {
+      float sum[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 pv = __ldg(p4 + j), qv = __ldg(q4 + j);
-              v[4 * j + 0] = silu_fast(pv.x + qv.x + radial * s_wr[col0 + 4 * j + 0]);
-              v[4 * j + 1] = silu_fast(pv.y + qv.y + radial * s_wr[col0 + 4 * j + 1]);
-              v[4 * j + 2] = silu_fast(pv.z + qv.z + radial * s_wr[col0 + 4 * j + 2]);
-              v[4 * j + 3] = silu_fast(pv.w + qv.w + radial * s_wr[col0 + 4 * j + 3]);
-            }
-          } else {
+      for (int j = 0; j < 16; ++j) sum[j] = ed.valid ? v[j] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          }
-          if (a.n_msg == 0) {
+      for (int off = 1; off < 32; off <<= 1) {
+        float t[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float sum = seg_scan(v[j], lane, seg_start);
-              if (is_tail && valid) atomicAdd(a.agg + (int64_t)src * M + col0 + j, sum);
-            }
-          }
-          push(a_col + (uint32_t)col0, v);
-        }
+        for (int j = 0; j < 16; ++j) t[j] = __shfl_up_sync(0xffffffffu, sum[j], off);
+        const bool take = lane - off >= ed.seg_start;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum[j] += take ? t[j] : 0.f;
       }
+      if (ed.is_tail && ed.valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red_add_v4(target_row + 4 * j, sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+      }
+    };
+    // chunk c of the first activation of a tile: silu(P[src] + Q[dst] + radial * w_r) -> A operand at a_col
+    auto prefetch_first = [&](const Edge& ed, int c) {
+      if (ed.valid) {
+        prefetch_l1(a.P + (int64_t)ed.src * M + c * 64 + hh * 16);
+        prefetch_l1(a.Q + (int64_t)ed.dst * M + c * 64 + hh * 16);
+      }
+    };
+    auto first_activation_chunk = [&](const Edge& ed, int c, uint32_t a_col) {
+      const int col0 = c * 64 + hh * 16;
+      float v[16];
+      if (ed.valid) {
+        const float4* p4 = reinterpret_cast<const float4*>(a.P + (int64_t)ed.src * M + col0);
+        const float4* q4 = reinterpret_cast<const float4*>(a.Q + (int64_t)ed.dst * M + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = __ldg(p4 + j), qv = __ldg(q4 + j), wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
+          v[4 * j + 0] = silu_fast(pv.x + qv.x + ed.radial * wv.x);
+          v[4 * j + 1] = silu_fast(pv.y + qv.y + ed.radial * wv.y);
+          v[4 * j + 2] = silu_fast(pv.z + qv.z + ed.radial * wv.z);
+          v[4 * j + 3] = silu_fast(pv.w + qv.w + ed.radial * wv.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (a.n_msg == 0) segment_add16(ed, v, a.agg + (int64_t)ed.src * M + col0);  // no hidden layer: this IS the message
+      push(a_col + (uint32_t)col0, v);
+    };
 
+    const int nk0 = M / 64;
+    const int n_last = p.gN[p.n_gemms - 1] / 64;   // chunks of the last accumulator
+    Edge cur{};
+    if (n_iterations > 0) {
+      cur = load_edge(0);
+      const uint32_t a_col = ((gc & 1u) ^ 1u) * kMaxN;
+      prefetch_first(cur, 0);
+      for (int c = 0; c < nk0; ++c) {
+        if (c + 1 < nk0) prefetch_first(cur, c + 1);
+        first_activation_chunk(cur, c, a_col);
+      }
+    }
+    for (int it = 0; it < n_iterations; ++it) {
       // ---- the chain of Linear layers ----
       float dot = 0.f;
+      Edge next{};
+      const bool has_next = it + 1 < n_iterations;
       for (int g = 0; g < p.n_gemms; ++g, ++gc) {
         const bool is_message = (g == a.n_msg - 1);
         const bool is_last = (g == p.n_gemms - 1);
         const uint32_t d_col = (gc & 1u) * kMaxN;
         const int nchunks = p.gN[g] / 64, nh = p.gN[g] / 2;
-        const float* bias = s_bias + g * kMaxN;
+        const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
+        if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
+          next = load_edge(it + 1);
+          prefetch_first(next, 0);
+        }
         int waited = -1;
         for (int c = 0; c < nchunks; ++c) {
           const int need = (c * 64 + 64 <= nh) ? 0 : 1;
@@ -476,41 +531,59 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_ts_kernel(const EdgeTcA
           float v[16];
           tmem_ld16(lane_taddr + d_col + col0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j] + bias[col0 + j]);
-          if (is_message) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float sum = seg_scan(valid ? v[j] : 0.f, lane, seg_start);
-              if (is_tail && valid) atomicAdd(a.agg + (int64_t)src * M + col0 + j, sum);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
+            v[4 * j + 0] = silu_fast(v[4 * j + 0] + b.x);
+            v[4 * j + 1] = silu_fast(v[4 * j + 1] + b.y);
+            v[4 * j + 2] = silu_fast(v[4 * j + 2] + b.z);
+            v[4 * j + 3] = silu_fast(v[4 * j + 3] + b.w);
           }
-          if (is_last) {
+          if (is_message) segment_add16(cur, v, a.agg + (int64_t)cur.src * M + col0);  // agg[src] += m (models/egnn.py:178-181)
+          if (is_last) {  // last coordinate layer: Linear(Cx -> 1, no bias)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dot = fmaf(v[j], s_wlast[col0 + j], dot);
+            for (int j = 0; j < 4; ++j) {
+              const float4 w = lds128(sa_wlast + (uint32_t)(col0 + 4 * j) * 4u);
+              dot = fmaf(v[4 * j + 0], w.x, dot);
+              dot = fmaf(v[4 * j + 1], w.y, dot);
+              dot = fmaf(v[4 * j + 2], w.z, dot);
+              dot = fmaf(v[4 * j + 3], w.w, dot);
+            }
+            // these accumulator columns are free now: the next tile's first activation goes there IN PLACE, so its
+            // first GEMM starts while this tile is being finished
+            if (has_next && c < nk0) {
+              if (c + 1 < nk0) prefetch_first(next, c + 1);
+              first_activation_chunk(next, c, d_col);
+            }
           } else {
             push(d_col + (uint32_t)col0, v);
           }
         }
+        if (is_last && has_next)
+          for (int c = n_last; c < nk0; ++c) {   // message width > coordinate width: columns no accumulator used
+            if (c + 1 < nk0) prefetch_first(next, c + 1);
+            first_activation_chunk(next, c, d_col);
+          }
       }
       // an fp16 overflow anywhere in the chain has turned into inf / NaN by now (see pack_f16x2_inf)
-      if (valid && !(fabsf(dot) <= CUDART_MAX_NORMAL_F)) poisoned = true;
+      if (cur.valid && !(fabsf(dot) <= CUDART_MAX_NORMAL_F)) poisoned = true;
 
-      // ---- coordinate update: xagg[src] += (x_src - x_dst) * phi_x(m) ----
-      atomicAdd(&s_dot[row], dot);
+      // ---- coordinate update: xagg[src] += (x_src - x_dst) * phi_x(m)   (models/egnn.py:189-215) ----
+      float* dot_slot = s_dot + (it & 1) * 4 * kTileM;   // [parity][hh][row]: one barrier per tile is enough
+      dot_slot[hh * kTileM + row] = dot;
       epilogue_barrier();
-      if (hh == 0) {
-        float phi = s_dot[row];
+      {
+        float phi = (dot_slot[row] + dot_slot[kTileM + row]) + (dot_slot[2 * kTileM + row] + dot_slot[3 * kTileM + row]);
         if (a.tanh_out) phi = tanhf(phi);
         float norm = 1.0f;
-        if (a.normalize) norm = tanhf(radial) / sqrtf(radial + 1e-16f);
-        for (int d = 0; d < a.D; ++d) {
+        if (a.normalize) norm = tanhf(cur.radial) / sqrtf(cur.radial + 1e-16f);  // models/egnn.py:240-264, epsilon = 1e-8
+        for (int d = hh; d < a.D; d += kEpiParts) {   // the coordinate columns are dealt over the four warps of a row
           float t = 0.f;
-          if (valid) t = (a.xcur[(int64_t)src * a.D + d] - a.xcur[(int64_t)dst * a.D + d]) * norm * phi;
-          const float sum = seg_scan(t, lane, seg_start);
-          if (is_tail && valid) atomicAdd(a.xagg + (int64_t)src * a.D + d, sum);
+          if (cur.valid) t = (a.xcur[(int64_t)cur.src * a.D + d] - a.xcur[(int64_t)cur.dst * a.D + d]) * norm * phi;
+          const float sum = seg_scan(t, lane, cur.seg_start);
+          if (cur.is_tail && cur.valid) atomicAdd(a.xagg + (int64_t)cur.src * a.D + d, sum);
         }
       }
-      epilogue_barrier();
+      cur = next;
     }
     if (poisoned && a.status) atomicOr(a.status, (int)B200MD_STATUS_TC_RANGE);
   }
