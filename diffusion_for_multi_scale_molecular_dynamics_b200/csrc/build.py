@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objects.append(obj)
         stale = force or not os.path.isfile(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src_path), header_time)
         if stale:
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src_path, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("B200MD_EXTRA_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", src_path, "-o", obj]
             jobs.append(cmd)
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
         results = list(pool.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs))

@@ -7,22 +7,25 @@
 // touches shared memory: no swizzled stores, no generic->async proxy fence, no A ring (its 64 KB go to a deeper weight
 // ring), and the tensor pipe reads only B from shared memory.
 //
-// Because A(g+1) stays in TMEM for the whole GEMM, the MMA order is N-half-major: the first half of the output
-// columns over all K chunks (as the epilogue delivers them), then the second half back to back; the epilogue of layer
-// g+1 starts on the first half while the tensor pipe still computes the second.  At the end of a tile the columns of
-// the last accumulator are reused the same way for the NEXT tile's first activation, so the tensor pipe never drains
-// between tiles.
+// Because A(g+1) stays in TMEM for the whole GEMM, the MMA order is column-group-major: the accumulator is computed
+// in kTsNSplit groups of N / kTsNSplit columns, the first group over all K chunks as the epilogue delivers them, the
+// others back to back.  With four groups (64 columns = one K chunk of the next layer each) the epilogue converts group
+// c while the tensor pipe computes group c + 1: the two run in lock-step instead of taking turns.  At the end of a
+// tile the columns of the last accumulator are reused the same way for the NEXT tile's first activation, so the
+// tensor pipe never drains between tiles.
 //   GEMM index n (running over tiles): D = buffer n & 1, A = buffer (n & 1) ^ 1 (2 x 256 columns = all of TMEM).
 //
 // Warps (10): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue: two per TMEM lane quarter,
-// each converting 32 of the 64 columns of a chunk.  Few, fat epilogue threads on purpose: with 10 warps a thread may
-// use 168 registers, enough to software-pipeline SiLU(chunk c+1) (SFU pipe) against the hi/lo split of chunk c
-// (ALU/FMA pipes) inside ONE instruction stream; 16 thin warps (96 registers) ran in phase and left both pipes idle
-// half of the time.
+// each converting 32 of the 64 columns of a chunk (few, fat epilogue threads: 168 registers each, 32 independent SiLU
+// chains per thread for the SFU pipe).
 #pragma once
 
-constexpr int kTsBStageBytes = 128 * kRowBytes;   // one weight part of a K chunk for HALF of the output columns (<= 16 KB)
-constexpr int kTsBStages = 12;
+#ifndef B200MD_TS_NSPLIT
+#define B200MD_TS_NSPLIT 2
+#endif
+constexpr int kTsNSplit = B200MD_TS_NSPLIT;       // column groups of an accumulator, computed one after the other
+constexpr int kTsBStageBytes = (kMaxN / kTsNSplit) * kRowBytes;   // one weight part of a K chunk for ONE column group
+constexpr int kTsBStages = 3 * kTsNSplit * 2;     // 192 KB in all
 constexpr int kTsSlots = 4;                       // K-chunk slots of the "A ready" barriers
 constexpr int kTsParts = 2;                       // epilogue warps per lane quarter
 constexpr int kTsCols = 64 / kTsParts;            // accumulator columns one epilogue thread converts per chunk
@@ -36,7 +39,7 @@ __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   TsSmem L;
   uint32_t o = 0;
   L.b = o; o += kTsBStages * kTsBStageBytes;
-  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 4) * 8;
+  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit) * 8;
   L.tmem_slot = o; o += 16;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
   L.wr = o; o += kMaxN * 4;
@@ -100,7 +103,10 @@ __device__ __forceinline__ uint32_t pack_f16x2_inf(float lo_elem, float hi_elem)
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
-// kTsCols activations -> per K step (16 values) [hi x 8 | lo x 8] packed fp16 pairs: the A-operand image of those columns
+// kTsCols activations -> per K step (16 values) [hi x 8 | -lo x 8] packed fp16 pairs: the A-operand image of those
+// columns.  hi = fp16(x); the second part holds fp16(hi - x) = -lo, one mixed-precision subtract per element
+// (sub.f32.f16, SASS FHADD) instead of an unpack and a subtract; the A_2 B_1 MMA negates it back (a_negate bit of the
+// instruction descriptor).
 __device__ __forceinline__ void split_hi_lo(const float (&v)[kTsCols], uint32_t (&w)[kTsCols]) {
 #pragma unroll
   for (int s = 0; s < kTsCols / 16; ++s)
@@ -108,29 +114,55 @@ __device__ __forceinline__ void split_hi_lo(const float (&v)[kTsCols], uint32_t 
     for (int i = 0; i < 8; ++i) {
       const float x0 = v[16 * s + 2 * i], x1 = v[16 * s + 2 * i + 1];
       const uint32_t hi = pack_f16x2_inf(x0, x1);
-      const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+      float n0, n1;
+      asm("{\n"
+          ".reg .b16 h0, h1;\n"
+          "mov.b32 {h0, h1}, %2;\n"
+          "sub.rn.f32.f16 %0, h0, %3;\n"
+          "sub.rn.f32.f16 %1, h1, %4;\n"
+          "}\n"
+          : "=f"(n0), "=f"(n1)
+          : "r"(hi), "f"(x0), "f"(x1));
       w[16 * s + i] = hi;
-      w[16 * s + 8 + i] = pack_f16x2_inf(x0 - back.x, x1 - back.y);
+      w[16 * s + 8 + i] = pack_f16x2_inf(n0, n1);
     }
 }
-// Scheduling pins (no instructions): pin_after makes every later use of v[] depend on `token` (a register written by
-// an earlier asm statement); pin_before makes v[] complete before the next volatile asm statement.
-__device__ __forceinline__ void pin_after(float (&v)[kTsCols], uint32_t token) {
-#pragma unroll
-  for (int i = 0; i < kTsCols; i += 16)
-    asm volatile(""
-                 : "+f"(v[i]), "+f"(v[i + 1]), "+f"(v[i + 2]), "+f"(v[i + 3]), "+f"(v[i + 4]), "+f"(v[i + 5]), "+f"(v[i + 6]),
-                   "+f"(v[i + 7]), "+f"(v[i + 8]), "+f"(v[i + 9]), "+f"(v[i + 10]), "+f"(v[i + 11]), "+f"(v[i + 12]),
-                   "+f"(v[i + 13]), "+f"(v[i + 14]), "+f"(v[i + 15])
-                 : "r"(token));
+constexpr uint32_t kIdescNegateA = 1u << 13;
+
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes per instruction) for the bias add and the SiLU arithmetic.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
 }
-__device__ __forceinline__ void pin_before(float (&v)[kTsCols]) {
-#pragma unroll
-  for (int i = 0; i < kTsCols; i += 16)
-    asm volatile(""
-                 : "+f"(v[i]), "+f"(v[i + 1]), "+f"(v[i + 2]), "+f"(v[i + 3]), "+f"(v[i + 4]), "+f"(v[i + 5]), "+f"(v[i + 6]),
-                   "+f"(v[i + 7]), "+f"(v[i + 8]), "+f"(v[i + 9]), "+f"(v[i + 10]), "+f"(v[i + 11]), "+f"(v[i + 12]),
-                   "+f"(v[i + 13]), "+f"(v[i + 14]), "+f"(v[i + 15]));
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// (silu(x0), silu(x1)) of a packed pair: x / (1 + 2^(-x log2 e)) with the SFU exp2 / reciprocal (about 2 ulp each, far
+// below the 1e-5 parity bound).  Moving the reciprocal to three Newton steps on the FMA pipe halves the SFU load but
+// does not change the launch time: at this point the kernel is limited by the 1000 W power cap, not by a pipe.
+__device__ __forceinline__ void silu2(uint64_t x, float& o0, float& o1) {
+  float t0, t1, e0, e1, r0, r1;
+  unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), t0, t1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+  unpack2(mul2(x, pack2(r0, r1)), o0, o1);
 }
 // shared-memory load by window address (keeps the access an LDS: pointers derived from the aligned dynamic-smem base
 // lose their address space and become generic loads)
@@ -145,6 +177,23 @@ __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ts_epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(kTsEpiWarps * 32) : "memory"); }
 
+// Optional cycle trace of CTA 0 (build with -DB200MD_TS_TRACE; read back with b200md_debug_ts_trace): one record
+// (warp, event, clock) per TS_TRACE call of lane 0 of the MMA warp and of the two epilogue warps of lane quarter 0.
+#ifdef B200MD_TS_TRACE
+constexpr int kTsTraceMax = 3 * 2048;     // 3 traced warps x 2048 records, each warp fills its own third (no atomics)
+__device__ uint4 g_ts_trace[kTsTraceMax];
+__device__ unsigned g_ts_trace_count;
+#define TS_TRACE(ev, arg)                                                                      \
+  do {                                                                                         \
+    if (trace_on && trace_idx < 2048u) {                                                       \
+      g_ts_trace[trace_slot * 2048u + trace_idx] = make_uint4((unsigned)warp, (unsigned)(ev), (unsigned)(arg), (unsigned)clock()); \
+      ++trace_idx;                                                                             \
+    }                                                                                          \
+  } while (0)
+#else
+#define TS_TRACE(ev, arg) do { } while (0)
+#endif
+
 struct TsPipe {
   uint32_t s_base, bar0, tmem_base;
   __device__ __forceinline__ uint32_t b_full(uint32_t s) const { return bar0 + 8u * s; }
@@ -153,8 +202,9 @@ struct TsPipe {
   __device__ __forceinline__ uint32_t a_full(uint32_t slot, uint32_t part) const {
     return bar0 + 8u * (2 * kTsBStages + slot * kTsParts + part);
   }
-  __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t half) const {
-    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + buf * 2 + half);
+  // "column group `group` of accumulator buffer `buf` is complete" (groups complete in order)
+  __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
+    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
   }
 };
 
@@ -188,7 +238,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     for (int s = 0; s < kTsBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), 1); }
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), 4);
-    for (int s = 0; s < 4; ++s) mbar_init(pipe.acc_full(s >> 1, s & 1), 1);
+    for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(pipe.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(pipe.s_base + L.tmem_slot, kTmemCols);
@@ -198,6 +248,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   pipe.tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
   const int n_iterations = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+#ifdef B200MD_TS_TRACE
+  bool trace_on = false;
+  unsigned trace_idx = 0;
+  const unsigned trace_slot = warp == 1 ? 0u : (warp == 4 ? 1u : 2u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_ts_trace_count = kTsTraceMax;
+#endif
 
   if (warp == 0) {
     // ===== weight producer =====
@@ -205,11 +261,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       uint32_t cb = 0;
       for (int it = 0; it < n_iterations; ++it)
         for (int g = 0; g < p.n_gemms; ++g) {
-          const int nk = p.gK[g] / 64, nh = p.gN[g] / 2;
+          const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsNSplit;
           const uint32_t bytes = (uint32_t)nh * kRowBytes;
           const int64_t part_floats = (int64_t)p.gN[g] * (kRowBytes / 4);
           const float* src = p.wtc + p.gW[g] + f16_image_offset(p.gK[g], p.gN[g]);
-          for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < kTsNSplit; ++h)
             for (int part = 0; part < 2 * nk; ++part, ++cb) {   // chunk 0 hi, chunk 0 lo, chunk 1 hi, ...
               const uint32_t s = cb % kTsBStages;
               mbar_wait(pipe.b_empty(s), ((cb / kTsBStages) & 1u) ^ 1u);
@@ -231,10 +287,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     uint32_t cb = 0, mca = 0, mgc = 0;
     for (int it = 0; it < n_iterations; ++it)
       for (int g = 0; g < p.n_gemms; ++g, ++mgc) {
-        const int nk = p.gK[g] / 64, nh = p.gN[g] / 2;
+#ifdef B200MD_TS_TRACE
+        trace_on = (blockIdx.x == 0 && lane == 0 && it >= 3 && it < 5);
+#endif
+        const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsNSplit;
         const uint32_t idesc = make_idesc(nh, 0u);
         const uint32_t d_col = (mgc & 1u) * kMaxN, a_col = d_col ^ kMaxN;
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kTsNSplit; ++h) {
           const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
           for (int c = 0; c < nk; ++c) {
             const uint32_t s1 = cb % kTsBStages, s2 = (cb + 1) % kTsBStages;
@@ -245,12 +304,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             const uint32_t a_chunk = tmem_base + a_col + (uint32_t)(c * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {   // K steps of 16
-              if (h == 0 && (j % (4 / kTsParts)) == 0)
+              if (h == 0 && (j % (4 / kTsParts)) == 0) {
+                TS_TRACE(100 + j, g * 16 + c);
                 mbar_wait(pipe.a_full(chunk % kTsSlots, j / (4 / kTsParts)), (chunk / kTsSlots) & 1u);
+                TS_TRACE(110 + j, g * 16 + c);
+              }
               tc_fence_after();
               if (leader) {
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);   // A_1 B_1
-                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc, 1u);         // A_2 B_1
+                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescNegateA, 1u);   // A_2 B_1 (A_2 is stored negated)
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);             // A_1 B_2
               }
             }
@@ -263,6 +325,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
           }
           if (leader) umma_commit(pipe.acc_full(mgc & 1u, h));
           __syncwarp();
+          TS_TRACE(120 + h, g);
         }
         mca += nk;
       }
@@ -275,7 +338,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     const uint32_t sa_bias = pipe.s_base + L.bias, sa_wr = pipe.s_base + L.wr, sa_wlast = pipe.s_base + L.wlast;
     uint32_t ca = 0, gc = 0;
     bool poisoned = false;
-
     // store the A-operand image of kTsCols columns at `col` of this lane and publish them
     auto publish = [&](uint32_t col, const uint32_t (&w)[kTsCols]) {
 #pragma unroll
@@ -346,15 +408,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       const int col0 = c * 64 + part * kTsCols;
       float v[kTsCols];
       if (ed.valid) {
+        const uint64_t rad2 = pack2(ed.radial, ed.radial);
         const float4* p4 = reinterpret_cast<const float4*>(a.P + (int64_t)ed.src * M + col0);
         const float4* q4 = reinterpret_cast<const float4*>(a.Q + (int64_t)ed.dst * M + col0);
 #pragma unroll
         for (int j = 0; j < kTsCols / 4; ++j) {
           const float4 pv = __ldg(p4 + j), qv = __ldg(q4 + j), wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
-          v[4 * j + 0] = silu_fast(pv.x + qv.x + ed.radial * wv.x);
-          v[4 * j + 1] = silu_fast(pv.y + qv.y + ed.radial * wv.y);
-          v[4 * j + 2] = silu_fast(pv.z + qv.z + ed.radial * wv.z);
-          v[4 * j + 3] = silu_fast(pv.w + qv.w + ed.radial * wv.w);
+          // silu((P + Q) + radial * w_r), two columns per instruction
+          silu2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), v[4 * j + 0], v[4 * j + 1]);
+          silu2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), v[4 * j + 2], v[4 * j + 3]);
         }
       } else {
 #pragma unroll
@@ -379,6 +441,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       }
     }
     for (int it = 0; it < n_iterations; ++it) {
+#ifdef B200MD_TS_TRACE
+      trace_on = (blockIdx.x == 0 && lane == 0 && q == 0 && it >= 3 && it < 5);
+#endif
       // ---- the chain of Linear layers ----
       float dot = 0.f;
       Edge next{};
@@ -387,7 +452,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         const bool is_message = (g == a.n_msg - 1);
         const bool is_last = (g == p.n_gemms - 1);
         const uint32_t d_col = (gc & 1u) * kMaxN;
-        const int nchunks = p.gN[g] / 64, nh = p.gN[g] / 2;
+        const int nchunks = p.gN[g] / 64, nh = p.gN[g] / kTsNSplit;
         const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
         if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
           next = load_edge(it + 1);
@@ -395,71 +460,50 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         }
         int waited = -1;
         auto wait_for_chunk = [&](int c) {
-          const int need = (c * 64 + 64 <= nh) ? 0 : 1;
+          const int need = (c * 64 + 64 + nh - 1) / nh - 1;   // last column group this chunk reads
           if (need > waited) {
+            TS_TRACE(1, g * 16 + c);
             mbar_wait(pipe.acc_full(gc & 1u, need), (gc >> 1) & 1u);
             tc_fence_after();
             waited = need;
+            TS_TRACE(2, g * 16 + c);
           }
         };
-        auto activate = [&](const uint32_t (&r)[kTsCols], int col0, float (&v)[kTsCols]) {   // v = silu(accumulator + bias)
+        // v = silu(accumulator + bias)
+        auto activate = [&](const uint32_t (&r)[kTsCols], int col0, float (&v)[kTsCols]) {
+          TS_TRACE(4, col0);
 #pragma unroll
           for (int j = 0; j < kTsCols / 4; ++j) {
             const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-            v[4 * j + 0] = silu_fast(__uint_as_float(r[4 * j + 0]) + b.x);
-            v[4 * j + 1] = silu_fast(__uint_as_float(r[4 * j + 1]) + b.y);
-            v[4 * j + 2] = silu_fast(__uint_as_float(r[4 * j + 2]) + b.z);
-            v[4 * j + 3] = silu_fast(__uint_as_float(r[4 * j + 3]) + b.w);
+            silu2(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
+            silu2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
           }
+          TS_TRACE(5, col0);
         };
         if (!is_last) {
-          // software pipeline: the SiLU of chunk c+1 (SFU pipe) sits in the same straight-line region as the hi/lo split
-          // of chunk c (ALU / FMA pipes), so the instruction scheduler overlaps them
           float v[kTsCols];
-          {
-            uint32_t r[kTsCols];
-            wait_for_chunk(0);
-            tmem_load_cols(lane_taddr + d_col + part * kTsCols, r);
-            activate(r, part * kTsCols, v);
-          }
-          for (int c = 0; c + 1 < nchunks; ++c) {
+          uint32_t r[kTsCols];
+          wait_for_chunk(0);
+          tmem_load_cols(lane_taddr + d_col + part * kTsCols, r);
+          activate(r, part * kTsCols, v);
+          for (int c = 0; c < nchunks; ++c) {
             const int col0 = c * 64 + part * kTsCols;
-            uint32_t r[kTsCols], w[kTsCols];
-            float nv[kTsCols];
-            wait_for_chunk(c + 1);
-            tmem_load_cols(lane_taddr + d_col + col0 + 64, r);
-            // SiLU(next chunk) and the hi/lo split of this chunk must end up in ONE straight-line region (between the
-            // tcgen05.wait::ld and the tcgen05.st) for the instruction scheduler to overlap the SFU pipe with the ALU/FMA
-            // pipes; left alone the optimiser rotates the split above the wait and the two run back to back
-            pin_after(v, r[0]);
+            const bool more = c + 1 < nchunks;
+            if (more) {   // the next chunk's accumulator columns travel while this chunk is split and published
+              wait_for_chunk(c + 1);
 #pragma unroll
-            for (int j = 0; j < kTsCols / 4; ++j) {
-              const float4 b = lds128(bias + (uint32_t)(col0 + 64 + 4 * j) * 4u);
-              nv[4 * j + 0] = silu_fast(__uint_as_float(r[4 * j + 0]) + b.x);
-              nv[4 * j + 1] = silu_fast(__uint_as_float(r[4 * j + 1]) + b.y);
-              nv[4 * j + 2] = silu_fast(__uint_as_float(r[4 * j + 2]) + b.z);
-              nv[4 * j + 3] = silu_fast(__uint_as_float(r[4 * j + 3]) + b.w);
-#pragma unroll
-              for (int i = 2 * j; i < 2 * j + 2; ++i) {   // pair i of this chunk: K step i / 8, slot i % 8
-                const float x0 = v[2 * i], x1 = v[2 * i + 1];
-                const uint32_t hi = pack_f16x2_inf(x0, x1);
-                const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-                w[16 * (i / 8) + (i % 8)] = hi;
-                w[16 * (i / 8) + 8 + (i % 8)] = pack_f16x2_inf(x0 - back.x, x1 - back.y);
-              }
+              for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(lane_taddr + d_col + col0 + 64 + 16 * i, r + 16 * i);
             }
-            pin_before(nv);
-            publish(d_col + (uint32_t)col0, w);
-            if (is_message) segment_add(cur, v, a.agg + (int64_t)cur.src * M + col0);  // agg[src] += m (models/egnn.py:178-181)
-#pragma unroll
-            for (int j = 0; j < kTsCols; ++j) v[j] = nv[j];
-          }
-          {
-            const int col0 = (nchunks - 1) * 64 + part * kTsCols;
             uint32_t w[kTsCols];
             split_hi_lo(v, w);
             publish(d_col + (uint32_t)col0, w);
-            if (is_message) segment_add(cur, v, a.agg + (int64_t)cur.src * M + col0);
+            TS_TRACE(6, g * 16 + c);
+            if (is_message) segment_add(cur, v, a.agg + (int64_t)cur.src * M + col0);  // agg[src] += m (models/egnn.py:178-181)
+            if (more) {
+#pragma unroll
+              for (int i = 0; i < kTsCols / 16; ++i) tmem_ld_wait16(r + 16 * i);
+              activate(r, col0 + 64, v);
+            }
           }
         } else {
           for (int c = 0; c < nchunks; ++c) {
@@ -498,7 +542,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       // ---- coordinate update: xagg[src] += (x_src - x_dst) * phi_x(m)   (models/egnn.py:189-215) ----
       float* dot_slot = s_dot + (it & 1) * kTsParts * kTileM;   // [parity][part][row]: one barrier per tile is enough
       dot_slot[part * kTileM + row] = dot;
+      TS_TRACE(7, it);
       ts_epilogue_barrier();
+      TS_TRACE(8, it);
       {
         float phi = 0.f;
 #pragma unroll

@@ -259,6 +259,23 @@ int pack_weight_image(const float* wt, int K, int N, float* dst, cudaStream_t st
 }
 }  // namespace tc
 
+#ifdef B200MD_TS_TRACE
+}  // namespace b200md
+// debug only: copy the cycle trace of the last egnn_edge_ts_kernel launches to the host and reset it
+extern "C" int b200md_debug_ts_trace(unsigned* out_records_u4, int max_records) {
+  unsigned n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, b200md::g_ts_trace_count, sizeof(n));
+  if (n > (unsigned)b200md::kTsTraceMax) n = b200md::kTsTraceMax;
+  if ((int)n > max_records) n = max_records;
+  cudaMemcpyFromSymbol(out_records_u4, b200md::g_ts_trace, sizeof(uint4) * n);
+  unsigned zero = 0;
+  cudaMemcpyToSymbol(b200md::g_ts_trace_count, &zero, sizeof(zero));
+  return (int)n;
+}
+namespace b200md {
+#endif
+
 int tc_sm_count() {
   static int n_sm = 0;
   if (n_sm == 0) {

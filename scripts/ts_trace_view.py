@@ -1,0 +1,16 @@
+#!/usr/bin/env python
+"""Render a cycle trace written by scripts/ts_trace.py as a three-column timeline (MMA warp | epilogue part 0 | part 1)."""
+import sys
+
+import numpy as np
+
+rec = np.loadtxt(sys.argv[1], dtype=np.int64)
+lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (0, 300)
+# the buffer holds the LAST launch that wrote each slot; clocks are 32-bit
+t0 = rec[rec[:, 0] == 1][:, 3].min()
+names = {1: 'acc_wait', 2: 'acc_ready', 3: 'tok_req', 4: 'tok_got', 5: 'act_done', 6: 'published', 7: 'tile_bar', 8: 'tile_bar_done',
+         100: 'A_wait0', 102: 'A_wait2', 110: 'A_got0', 112: 'A_got2', 120: 'h0_committed', 121: 'h1_committed'}
+evs = sorted((int((c - t0) & 0xffffffff), int(w), int(e), int(a)) for w, e, a, c in rec)
+for t, w, e, a in evs[lo:hi]:
+    col = {1: 0, 4: 34, 8: 68}.get(w, 100)
+    print(f"{t:8d} " + " " * col + f"{names.get(e, e)} {a}")
