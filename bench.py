@@ -45,7 +45,10 @@ TOTAL_TIME_STEPS = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set full`
 # captures (profiles/ncu_full_r01f.txt: egnn_edge_tc_kernel<3xFP16>, 4096 samples; the algorithmic minimum is
 # P + Q + xcur reads, agg read-modify-write and the edge list: about 0.86 GB)
-NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 874239488 + 254038784, ("cfg2", 4096, "f16x3"): 874239488 + 254038784}
+# dram__bytes_read.sum + dram__bytes_write.sum of one edge-kernel launch (ncu --set full, profiles/ncu_full_r01g.txt /
+# r01f.txt); the algorithmic HBM bytes of a launch are the P / Q / agg rows: 3 x samples x atoms x 1 KB = 805 MB
+NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 875473664 + 251433216, ("cfg2", 4096, "f16x3ts"): 875473664 + 251433216,
+                     ("cfg2", 4096, "f16x3"): 874239488 + 254038784}
 PRODUCTION = dict(n_layers=4, message_n_hidden_dimensions=4, message_hidden_dimensions_size=256,
                   node_n_hidden_dimensions=4, node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4,
                   coordinate_hidden_dimensions_size=256)
@@ -324,6 +327,10 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
                     "fp32_exact_passes": passes,
                     "fp32_exact_ceiling_tflops": ceiling,
                     "frac_of_fp32_exact_ceiling": (achieved / ceiling) if ceiling else None,
+                    # MMA FLOPs the tensor pipe actually executes (passes x executed share, in fp16-rate units) against
+                    # the same sustained dense peak: how close the kernel is to what the power-capped chip can issue
+                    "executed_dense_equivalent_tflops": (achieved * passes * executed_fraction / rate)
+                    if (rate and executed_fraction) else None,
                     "algorithmic_flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                     "share_of_step": edge_ms / total_class_ms if total_class_ms else None,
                     "class_ms_per_step": {k: v[0] / profile_steps for k, v in classes.items()},
