@@ -107,6 +107,77 @@ __global__ void pc_coordinates_update_kernel(const float* x, const float* __rest
   }
 }
 
+// ---- adaptive corrector (generators/adaptive_corrector.py:98-148) ------------------------------------------------
+// eps = 2 (r ||z|| / max(||sigma s|| / sigma, small_eps))^2 with
+//   ||sigma s|| = mean over samples of the L2 norm of the sample's whole score block (units x d values),
+//   ||z||       = mean over (sample, unit) of the L2 norm of the d-vector.
+// Two launches, both with a fixed reduction order (deterministic): per-sample partial norms, then one CTA.
+__global__ void adaptive_norms_kernel(const float* __restrict__ s, const float* __restrict__ z, int32_t units, int32_t d,
+                                      float* __restrict__ partial, int64_t n_samples) {
+  __shared__ float sh_s[32], sh_z[32];
+  const int64_t b = blockIdx.x;
+  const float* sb = s + b * units * d;
+  const float* zb = z + b * units * d;
+  float ss = 0.f, zn = 0.f;
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    float zz = 0.f;
+    for (int k = 0; k < d; ++k) {
+      const float sv = sb[u * d + k], zv = zb[u * d + k];
+      ss += sv * sv;
+      zz += zv * zv;
+    }
+    zn += sqrtf(zz);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) { ss += __shfl_down_sync(0xffffffffu, ss, o); zn += __shfl_down_sync(0xffffffffu, zn, o); }
+  if (lane == 0) { sh_s[warp] = ss; sh_z[warp] = zn; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nwarps = blockDim.x >> 5;
+    ss = lane < nwarps ? sh_s[lane] : 0.f;
+    zn = lane < nwarps ? sh_z[lane] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) { ss += __shfl_down_sync(0xffffffffu, ss, o); zn += __shfl_down_sync(0xffffffffu, zn, o); }
+    if (lane == 0) { partial[b] = sqrtf(ss); partial[n_samples + b] = zn; }
+  }
+}
+
+__global__ void adaptive_step_size_kernel(const float* __restrict__ partial, int64_t n_samples, int32_t units, float sigma,
+                                          float corrector_r, float small_epsilon, float* __restrict__ step_out) {
+  __shared__ float sh_s[32], sh_z[32];
+  float ss = 0.f, zn = 0.f;
+  for (int64_t b = threadIdx.x; b < n_samples; b += blockDim.x) { ss += partial[b]; zn += partial[n_samples + b]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) { ss += __shfl_down_sync(0xffffffffu, ss, o); zn += __shfl_down_sync(0xffffffffu, zn, o); }
+  if (lane == 0) { sh_s[warp] = ss; sh_z[warp] = zn; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nwarps = blockDim.x >> 5;
+    ss = lane < nwarps ? sh_s[lane] : 0.f;
+    zn = lane < nwarps ? sh_z[lane] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) { ss += __shfl_down_sync(0xffffffffu, ss, o); zn += __shfl_down_sync(0xffffffffu, zn, o); }
+    if (lane == 0) {
+      const float score_norm = (ss / (float)n_samples) / sigma;               // adaptive_corrector.py:130-134
+      const float z_norm = zn / ((float)n_samples * (float)units);            // :136
+      const float ratio = corrector_r * z_norm / fmaxf(score_norm, small_epsilon);
+      const float eps = 2.0f * ratio * ratio;                                  // :138-146
+      step_out[0] = eps;
+      step_out[1] = sqrtf(2.0f * eps);
+    }
+  }
+}
+
+// out = [wrap]((x + (w[0] * s) / sigma) + w[1] * z) with the two weights read from device memory
+__global__ void pc_update_device_weights_kernel(const float* x, const float* __restrict__ s, const float* __restrict__ z,
+                                                const float* __restrict__ weights, float sigma, int64_t n, int wrap,
+                                                float* out) {
+  const float sw = weights[0], nw = weights[1];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const float a = __fdiv_rn(__fmul_rn(sw, s[t]), sigma);
+    const float v = __fadd_rn(__fadd_rn(x[t], a), __fmul_rn(nw, z[t]));
+    out[t] = wrap ? wrap_unit(v) : v;
+  }
+}
+
 // Lattice update, generators/langevin_generator.py:485-490 (no wrap).  One thread per (sample, Philox block of 4),
 // the same block layout as draw_kernel with units = 1, unit_size = n_lp.
 __global__ void pc_lattice_update_kernel(const float* l, const float* __restrict__ s,
@@ -505,6 +576,30 @@ int b200md_pc_coordinates_update(const float* x, const float* s, const float* z,
       default: pc_coordinates_update_kernel<3><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
     }
   }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_adaptive_corrector_step_size(const float* s, const float* z, int64_t n_samples, int32_t units, int32_t d,
+                                        float sigma, float corrector_r, float small_epsilon, float* partial,
+                                        float* step_out, b200md_stream_t stream) {
+  if (!s || !z || !partial || !step_out || n_samples <= 0 || units <= 0 || d <= 0 || !(sigma > 0.f))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  const int threads = units >= 256 ? 256 : (units >= 64 ? 128 : 32);
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); adaptive_norms_kernel<<<(unsigned)n_samples, threads, 0, st>>>(s, z, units, d, partial, n_samples); }
+  B200MD_CHECK_LAUNCH();
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); adaptive_step_size_kernel<<<1, 1024, 0, st>>>(partial, n_samples, units, sigma, corrector_r, small_epsilon, step_out); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_pc_update_device_weights(const float* x, const float* s, const float* z, const float* weights, float sigma,
+                                    int64_t n_values, int32_t wrap, float* out, b200md_stream_t stream) {
+  if (!x || !s || !z || !weights || !out || n_values < 0 || !(sigma > 0.f)) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_values == 0) return B200MD_OK;
+  cudaStream_t st = as_stream(stream);
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); pc_update_device_weights_kernel<<<grid_for(n_values, 256), 256, 0, st>>>(x, s, z, weights, sigma, n_values, wrap, out); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }

@@ -1,0 +1,142 @@
+// Structure statistics built on the periodic-image sweep of graph.cu.
+//
+// b200md_pair_distances_{count,fill} replace compute_distances_in_batch (utils/structure_utils.py:41-121): all
+// interatomic distances 0 < d <= max_distance over the 27 periodic images, in the reference's native order
+// (structure, image, source atom, ascending distance).  It is the sample statistic of the reference's structure
+// Kolmogorov-Smirnov metric (models/axl_diffusion_lightning_model.py:531,633) and of the trajectory-level parity tests.
+// Same rounding chain as the radius graph (d2 in fp32 without FMA contraction); the reference filters on the distance
+// itself, `0 < sqrt(d2) <= max_distance` (structure_utils.py:113-121), so the test is made on the IEEE square root.
+#include "common.cuh"
+#include "graph.cuh"
+
+namespace b200md {
+
+__device__ __forceinline__ bool distance_hit(float xi, float yi, float zi, float xj, float yj, float zj, float lx,
+                                             float ly, float lz, float rc, float& d2, float& d) {
+  image_hit(xi, yi, zi, xj, yj, zj, lx, ly, lz, 0.f, d2);
+  d = __fsqrt_rn(d2);
+  return (d > 0.0f) && (d <= rc);
+}
+
+__global__ void pair_distances_count_kernel(const float* __restrict__ positions, const float* __restrict__ cell,
+                                            int relative, float rc, int32_t N, int32_t* __restrict__ counts,
+                                            int64_t* __restrict__ per_structure) {
+  extern __shared__ float smem[];
+  float* px = smem; float* py = px + N; float* pz = py + N;
+  float* lat = pz + N;  // [27][3]
+  __shared__ float s_cell[9];
+  __shared__ unsigned long long s_total;
+  const int64_t b = blockIdx.x;
+  stage_structure(positions + b * N * 3, cell + b * 9, relative, N, px, py, pz, lat, s_cell);
+  if (threadIdx.x == 0) s_total = 0ull;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  unsigned long long local = 0;
+  for (int r = warp; r < 27 * N; r += nwarps) {
+    const int img = r / N, i = r - img * N;
+    const float xi = px[i], yi = py[i], zi = pz[i];
+    const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
+    int n = 0;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      bool hit = false;
+      float d2, d;
+      if (j < N) hit = distance_hit(xi, yi, zi, px[j], py[j], pz[j], lx, ly, lz, rc, d2, d);
+      n += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == 0) { counts[(b * 27 + img) * N + i] = n; local += n; }
+  }
+  if (lane == 0 && local) atomicAdd(&s_total, local);
+  __syncthreads();
+  if (threadIdx.x == 0) per_structure[b] = (int64_t)s_total;
+}
+
+__global__ void pair_distances_fill_kernel(const float* __restrict__ positions, const float* __restrict__ cell,
+                                           int relative, float rc, int32_t N, const int64_t* __restrict__ offsets,
+                                           float* __restrict__ distances_out) {
+  extern __shared__ float smem[];
+  float* px = smem; float* py = px + N; float* pz = py + N;
+  float* lat = pz + N;          // [27][3]
+  float* scratch = lat + 81;    // per-warp [N] d2, [N] d, [N] j
+  __shared__ float s_cell[9];
+  const int64_t b = blockIdx.x;
+  stage_structure(positions + b * N * 3, cell + b * 9, relative, N, px, py, pz, lat, s_cell);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float* wd2 = scratch + (size_t)warp * 3 * N;
+  float* wd = wd2 + N;
+  int* wj = reinterpret_cast<int*>(wd + N);
+  for (int r = warp; r < 27 * N; r += nwarps) {
+    const int img = r / N, i = r - img * N;
+    const float xi = px[i], yi = py[i], zi = pz[i];
+    const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
+    int cnt = 0;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      bool hit = false;
+      float d2 = 0.f, d = 0.f;
+      if (j < N) hit = distance_hit(xi, yi, zi, px[j], py[j], pz[j], lx, ly, lz, rc, d2, d);
+      const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+      if (hit) { const int k = cnt + __popc(ballot & lt_mask); wd2[k] = d2; wd[k] = d; wj[k] = j; }
+      cnt += __popc(ballot);
+    }
+    __syncwarp();
+    const int64_t pos = offsets[(b * 27 + img) * N + i];
+    // rank by (d2, j): ascending squared distance like Kmin_argKmin (structure_utils.py:104-106)
+    for (int k = lane; k < cnt; k += 32) {
+      const float dk = wd2[k]; const int jk = wj[k];
+      int rank = 0;
+      for (int m = 0; m < cnt; ++m) {
+        const float dm = wd2[m];
+        rank += (dm < dk) || (dm == dk && wj[m] < jk);
+      }
+      distances_out[pos + rank] = wd[k];
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace b200md
+
+using namespace b200md;
+
+extern "C" {
+
+int b200md_pair_distances_count(const float* positions, const float* cell, int32_t positions_are_relative,
+                                float max_distance, int64_t n_samples, int32_t n_atoms, int32_t* counts,
+                                int64_t* distances_per_structure, b200md_stream_t stream) {
+  if (!positions || !cell || !counts || !distances_per_structure || n_samples < 0 || n_atoms <= 0 || !(max_distance > 0.f))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_atoms > 4096) return B200MD_ERR_UNSUPPORTED;
+  if (n_samples == 0) return B200MD_OK;
+  const int threads = n_atoms >= 256 ? 256 : (n_atoms >= 64 ? 128 : 64);
+  const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(pair_distances_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); pair_distances_count_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+      positions, cell, positions_are_relative, max_distance, n_atoms, counts, distances_per_structure); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_pair_distances_fill(const float* positions, const float* cell, int32_t positions_are_relative,
+                               float max_distance, int64_t n_samples, int32_t n_atoms, const int64_t* offsets,
+                               float* distances_out, b200md_stream_t stream) {
+  if (!positions || !cell || !offsets || !distances_out || n_samples < 0 || n_atoms <= 0 || !(max_distance > 0.f))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_atoms > 4096) return B200MD_ERR_UNSUPPORTED;
+  if (n_samples == 0) return B200MD_OK;
+  int threads = n_atoms >= 256 ? 256 : (n_atoms >= 64 ? 128 : 64);
+  if (n_atoms > 512) threads = 128;
+  const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float) + (size_t)(threads / 32) * 3 * n_atoms * sizeof(float);
+  if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(pair_distances_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); pair_distances_fill_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+      positions, cell, positions_are_relative, max_distance, n_atoms, offsets, distances_out); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+}  // extern "C"

@@ -1,6 +1,7 @@
 """Generator factory (reference: generators/instantiate_generator.py:25-82) for the predictor-corrector branch."""
 from typing import Optional
 
+from diffusion_for_multi_scale_molecular_dynamics_b200.generators.adaptive_corrector import AdaptiveCorrectorGenerator
 from diffusion_for_multi_scale_molecular_dynamics_b200.generators.axl_generator import SamplingParameters
 from diffusion_for_multi_scale_molecular_dynamics_b200.generators.constrained_langevin_generator import \
     ConstrainedLangevinGenerator
@@ -18,14 +19,22 @@ def instantiate_generator(
     trajectory_initializer: Optional[TrajectoryInitializer] = None,
     sampling_constraints: Optional[SamplingConstraint] = None,
 ):
-    """Build the generator named by ``sampling_parameters.algorithm``; only "predictor_corrector" is on this path."""
-    if sampling_parameters.algorithm != "predictor_corrector":
-        raise NotImplementedError(
-            f"Generator type {sampling_parameters.algorithm} is not part of the sm_100a sampling path "
-            "(predictor_corrector only).")
-    if sampling_constraints is None:
+    """Build the generator named by ``sampling_parameters.algorithm``: "predictor_corrector" and "adaptive_corrector"
+    are on this path; the ODE / SDE solvers of the reference are not."""
+    assert sampling_parameters.algorithm in ["ode", "sde", "predictor_corrector", "adaptive_corrector"], \
+        "Unknown algorithm. Possible choices are 'ode', 'sde', 'predictor_corrector' and 'adaptive_corrector'"
+    if sampling_constraints is not None:
+        assert sampling_parameters.algorithm == "predictor_corrector", \
+            "Only the 'predictor_corrector' scheme supports sampling constraints."
+        return ConstrainedLangevinGenerator(noise_parameters=noise_parameters, sampling_parameters=sampling_parameters,
+                                            axl_network=axl_network, sampling_constraints=sampling_constraints,
+                                            trajectory_initializer=trajectory_initializer)
+    if sampling_parameters.algorithm == "predictor_corrector":
         return LangevinGenerator(noise_parameters=noise_parameters, sampling_parameters=sampling_parameters,
                                  axl_network=axl_network, trajectory_initializer=trajectory_initializer)
-    return ConstrainedLangevinGenerator(noise_parameters=noise_parameters, sampling_parameters=sampling_parameters,
-                                        axl_network=axl_network, sampling_constraints=sampling_constraints,
-                                        trajectory_initializer=trajectory_initializer)
+    if sampling_parameters.algorithm == "adaptive_corrector":
+        return AdaptiveCorrectorGenerator(noise_parameters=noise_parameters, sampling_parameters=sampling_parameters,
+                                          axl_network=axl_network, trajectory_initializer=trajectory_initializer)
+    raise NotImplementedError(
+        f"Generator type {sampling_parameters.algorithm} is not part of the sm_100a sampling path "
+        "(predictor_corrector and adaptive_corrector only).")

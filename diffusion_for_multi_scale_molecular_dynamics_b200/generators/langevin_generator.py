@@ -36,6 +36,16 @@ def _as_float(value) -> float:
     return float(value.item()) if isinstance(value, torch.Tensor) else float(value)
 
 
+def _on_device(value) -> bool:
+    return torch.is_tensor(value) and value.is_cuda
+
+
+def _device_weights(score_weight, noise_weight, device: torch.device) -> torch.Tensor:
+    """(score weight, noise weight) as a 2-float device tensor, without a host round trip for device inputs."""
+    parts = [torch.as_tensor(w, dtype=torch.float32, device=device).reshape(-1)[:1] for w in (score_weight, noise_weight)]
+    return torch.cat(parts).contiguous()
+
+
 class LangevinGenerator(PredictorCorrectorAXLGenerator):
     """Annealed Langevin dynamics (Song & Ermon 2019) with D3PM atom types, as in the reference."""
 
@@ -198,6 +208,12 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
         s = _cabi.as_f32(sigma_normalized_scores)
         zz = _cabi.as_f32(z.to(device))
         out = torch.empty_like(x)
+        if _on_device(score_weight) or _on_device(gaussian_noise_weight):  # e.g. the adaptive corrector's step size
+            weights = _device_weights(score_weight, gaussian_noise_weight, device)
+            _cabi.check(_cabi.lib().b200md_pc_update_device_weights(
+                _cabi.ptr(x), _cabi.ptr(s), _cabi.ptr(zz), _cabi.ptr(weights), _as_float(sigma_i), x.numel(), 1,
+                _cabi.ptr(out), _cabi.stream_ptr(device)))
+            return out
         _cabi.check(_cabi.lib().b200md_pc_coordinates_update(
             _cabi.ptr(x), _cabi.ptr(s), _cabi.ptr(zz), _as_float(score_weight), _as_float(sigma_i),
             _as_float(gaussian_noise_weight), number_of_samples, number_of_atoms, d, self._active_seed, self._step_id,
@@ -270,6 +286,12 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
         s = _cabi.as_f32(sigma_normalized_scores)
         zz = _cabi.as_f32(z.to(device))
         out = torch.empty_like(lattice)
+        if _on_device(score_weight) or _on_device(gaussian_noise_weight):
+            weights = _device_weights(score_weight, gaussian_noise_weight, device)
+            _cabi.check(_cabi.lib().b200md_pc_update_device_weights(
+                _cabi.ptr(lattice), _cabi.ptr(s), _cabi.ptr(zz), _cabi.ptr(weights), _as_float(sigma_n_i),
+                lattice.numel(), 0, _cabi.ptr(out), _cabi.stream_ptr(device)))
+            return out
         _cabi.check(_cabi.lib().b200md_pc_lattice_update(
             _cabi.ptr(lattice), _cabi.ptr(s), _cabi.ptr(zz), _as_float(score_weight), _as_float(sigma_n_i),
             _as_float(gaussian_noise_weight), number_of_samples, n_lp, self._active_seed, self._step_id,

@@ -122,6 +122,23 @@ int b200md_pc_lattice_update(const float* l, const float* sigma_normalized_score
                              b200md_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * AdaptiveCorrectorGenerator._generic_corrector_step_size (generators/adaptive_corrector.py:98-148):
+ *   eps = 2 (r ||z|| / max(||sigma s|| / sigma, small_epsilon))^2
+ * ||sigma s|| = mean over samples of the L2 norm of the sample's score block [units, d]; ||z|| = mean over
+ * (sample, unit) of the L2 norm of the d-vector (coordinates: units = atoms, d = 3; lattice: units = 1, d = 6).
+ * partial: workspace of 2 * n_samples floats.  step_out [2] (device) = (eps, sqrt(2 eps)): the score and noise
+ * weights of the corrector update, consumed by b200md_pc_update_device_weights without a host round trip.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_adaptive_corrector_step_size(const float* sigma_normalized_score, const float* z,
+                                        int64_t n_samples, int32_t units, int32_t d, float sigma,
+                                        float corrector_r, float small_epsilon, float* partial,
+                                        float* step_out, b200md_stream_t stream);
+/* out = [wrap]((x + (weights[0] * s) / sigma) + weights[1] * z), elementwise over n_values; weights on the device. */
+int b200md_pc_update_device_weights(const float* x, const float* sigma_normalized_score, const float* z,
+                                    const float* weights, float sigma, int64_t n_values, int32_t wrap,
+                                    float* out, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LangevinGenerator._atom_types_update (langevin_generator.py:247-439) fused with
  * get_probability_at_previous_time_step / get_probability_from_logits (utils/d3pm_utils.py:64-150).
  * q / q_bar / q_bar_tm1 are the [C,C] matrices of the current time index (device pointers into the
@@ -222,6 +239,25 @@ int b200md_radius_graph_fill(const float* positions, const float* cell,
                              int64_t node_index_offset, int64_t* src_out, int64_t* dst_out,
                              float* shifts_out_or_null, int64_t* edge_batch_or_null,
                              b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pair distances: compute_distances_in_batch (utils/structure_utils.py:41-121), the sample statistic of the
+ * reference's structure Kolmogorov-Smirnov metric (models/axl_diffusion_lightning_model.py:531,633).
+ *
+ * All distances d with 0 < d <= max_distance between atom i and the periodic images (n in {-1,0,1}^3) of
+ * atom j, in the reference's order (structure, image, i, ascending d2, ties by j).  d2 follows the rounding
+ * chain of the radius graph; the filter is made on d = sqrt(d2) as the reference does (:113-121).
+ * count: counts [B*27*N] int32 and distances_per_structure [B] int64.
+ * fill : offsets = exclusive scan of counts (int64) -> distances_out [sum(counts)] f32.
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_pair_distances_count(const float* positions, const float* cell,
+                                int32_t positions_are_relative, float max_distance, int64_t n_samples,
+                                int32_t n_atoms, int32_t* counts, int64_t* distances_per_structure,
+                                b200md_stream_t stream);
+int b200md_pair_distances_fill(const float* positions, const float* cell,
+                               int32_t positions_are_relative, float max_distance, int64_t n_samples,
+                               int32_t n_atoms, const int64_t* offsets, float* distances_out,
+                               b200md_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * EGNN score network: EGNNScoreNetwork._forward_unchecked (models/score_networks/egnn_score_network.py:226-303)

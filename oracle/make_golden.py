@@ -313,6 +313,64 @@ def golden_analytical():
     save("analytical", **out)
 
 
+def golden_pair_distances():
+    """compute_distances_in_batch (utils/structure_utils.py:41-121) of the unmodified reference."""
+    from diffusion_for_multi_scale_molecular_dynamics.utils.structure_utils import compute_distances_in_batch
+    torch.manual_seed(21)
+    out = {}
+    B, N = 4, 14
+    basis = torch.diag_embed(5.0 + 2.0 * torch.rand(B, 3)) + 0.4 * (torch.rand(B, 3, 3) - 0.5)
+    cart = torch.matmul(torch.rand(B, N, 3), basis)
+    out["tri.cart"], out["tri.basis"] = cart, basis
+    for rc in (1.7, 2.6):
+        out[f"tri.distances_rc{rc}"] = compute_distances_in_batch(cart, basis, rc)
+    # thermally displaced diamond silicon, 2x2x2 conventional cells
+    basis_atoms = torch.tensor([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [.25, .25, .25], [.25, .75, .75],
+                                [.75, .25, .75], [.75, .75, .25]])
+    grid = torch.stack(torch.meshgrid(*[torch.arange(2)] * 3, indexing="ij"), dim=-1).reshape(-1, 1, 3)
+    rel = ((grid + basis_atoms.unsqueeze(0)) / 2).reshape(1, -1, 3).repeat(3, 1, 1)
+    rel = torch.remainder(rel + 0.01 * torch.randn_like(rel), 1.0)
+    cell = torch.diag_embed(torch.full((3, 3), 10.86))
+    cart = torch.matmul(rel, cell)
+    out["si.cart"], out["si.basis"] = cart, cell
+    out["si.distances_rc5.0"] = compute_distances_in_batch(cart, cell, 5.0)
+    save("pair_distances", **out)
+
+
+def golden_adaptive_corrector():
+    """AdaptiveCorrectorGenerator (generators/adaptive_corrector.py:17-148) of the unmodified reference: the step-size
+    formula on random inputs, and a short corrector-only trajectory with injected noise."""
+    from diffusion_for_multi_scale_molecular_dynamics.generators.adaptive_corrector import AdaptiveCorrectorGenerator
+    out = {}
+    variant, B, N, a, T, n_corr = "radial_sige", 3, 16, 7.0, 5, 2
+    net = make_network(variant, seed=310)
+    num_atom_types = EGNN_VARIANTS[variant]["num_atom_types"]
+    noise_parameters = NoiseParameters(total_time_steps=T, sigma_min=0.005, sigma_max=0.5, corrector_r=0.17)
+    sampling = PredictorCorrectorSamplingParameters(
+        algorithm="adaptive_corrector", number_of_samples=B, number_of_atoms=N, num_atom_types=num_atom_types,
+        number_of_corrector_steps=n_corr, use_fixed_lattice_parameters=True, cell_dimensions=[a, a, a])
+    gen = AdaptiveCorrectorGenerator(noise_parameters, sampling, net)
+    torch.manual_seed(410)
+    for tag, shape, n_dim, sigma in (("x", (5, 12, 3), 3, 0.07), ("l", (5, 6), 2, 0.03), ("tiny", (2, 4, 3), 3, 0.5)):
+        scores = torch.randn(*shape) * (1e-12 if tag == "tiny" else 0.3)   # "tiny" exercises the small_epsilon clip
+        z = torch.randn(*shape)
+        out[f"step.{tag}.scores"], out[f"step.{tag}.z"], out[f"step.{tag}.sigma"] = scores, z, torch.tensor(sigma)
+        out[f"step.{tag}.eps"] = gen._generic_corrector_step_size(2, torch.tensor(sigma), scores, z, n_dim=n_dim)
+    x0 = torch.rand(B, N, 3)
+    a0 = torch.full((B, N), num_atom_types, dtype=torch.long)
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = a
+    tape = NoiseTape(seed=79)
+    with torch.no_grad(), TapedHooks(gen, tape):
+        final = gen.sample_from_noisy_composition(AXL(A=a0.clone(), X=x0.clone(), L=lattice.clone()), T, 0)
+    for key, value in net.state_dict().items():
+        out[f"traj.sd.{key}"] = value
+    out["traj.x0"], out["traj.a0"], out["traj.l"] = x0, a0, lattice
+    out["traj.final_a"], out["traj.final_x"] = final.A, final.X
+    out["traj.T"], out["traj.n_corr"] = T, n_corr
+    save("adaptive_corrector", **out)
+
+
 def golden_checkpoint():
     """A checkpoint shaped like the reference's Lightning checkpoints: ``state_dict`` keys under ``axl_network.`` and the
     reference's own parameter dataclass pickled (by class name) inside ``hyper_parameters``."""
@@ -328,12 +386,9 @@ def golden_checkpoint():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    golden_noise_tables()
-    golden_wrap_and_score()
-    golden_neighbors()
-    golden_segment()
-    golden_egnn()
-    golden_atom_types()
-    golden_trajectories()
-    golden_analytical()
-    golden_checkpoint()
+    ALL = [golden_noise_tables, golden_wrap_and_score, golden_neighbors, golden_segment, golden_egnn, golden_atom_types,
+           golden_trajectories, golden_analytical, golden_checkpoint, golden_pair_distances, golden_adaptive_corrector]
+    wanted = sys.argv[1:]   # e.g. `python oracle/make_golden.py pair_distances`; no argument = everything
+    for fn in ALL:
+        if not wanted or fn.__name__.replace("golden_", "") in wanted:
+            fn()

@@ -19,6 +19,7 @@ import itertools
 import math
 from typing import Callable, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -202,6 +203,28 @@ def periodic_adjacency(cartesian_positions: torch.Tensor, basis_vectors: torch.T
     adjacency = torch.tensor([src_l, dst_l], dtype=torch.int64).reshape(2, -1)
     shifts = torch.stack(shift_l) if shift_l else torch.zeros(0, 3, dtype=cartesian_positions.dtype)
     return adjacency, shifts, torch.tensor(batch_l, dtype=torch.int64), counts
+
+
+def compute_distances_in_batch(cartesian_positions: torch.Tensor, unit_cell: torch.Tensor, max_distance: float,
+                               ieee_sqrt: bool = False):
+    """compute_distances_in_batch (utils/structure_utils.py:41-121), dense semantics: all distances 0 < d <= max_distance
+    over the 27 images, flattened in (batch, image, source, ascending d^2 -- ties by destination) order.
+
+    ``torch.sqrt`` on CPU is a vectorised approximation that differs from the correctly rounded square root in ~0.6 % of
+    fp32 inputs (by one ulp); ``ieee_sqrt=True`` takes numpy's correctly rounded one instead, which is what CUDA's
+    ``sqrtf`` (and therefore the reference run on a GPU) returns."""
+    B, N, _ = cartesian_positions.shape
+    rc = torch.tensor(max_distance, dtype=cartesian_positions.dtype)
+    images = relative_lattice_vectors().to(cartesian_positions.dtype)
+    lattice_vectors = torch.stack([_fp32_chain_matmul3(images, unit_cell[b]) for b in range(B)])  # [B,27,3]
+    shifted = cartesian_positions[:, None, :, :] + lattice_vectors[:, :, None, :]
+    diff = cartesian_positions[:, None, :, None, :] - shifted[:, :, None, :, :]  # [B,27,N(i),N(j),3]
+    sq = diff * diff
+    d2 = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+    order = torch.argsort(d2, dim=-1, stable=True)  # Kmin_argKmin: ascending d^2
+    sorted_d2 = torch.gather(d2, -1, order)
+    distances = (torch.from_numpy(np.sqrt(sorted_d2.numpy())) if ieee_sqrt else torch.sqrt(sorted_d2)).flatten()  # :110
+    return distances[torch.logical_and(distances > 0.0, distances <= rc)]  # :113-121
 
 
 def periodic_pair_mask(relative_coordinates: torch.Tensor, unit_cell: torch.Tensor, radial_cutoff: float):

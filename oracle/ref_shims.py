@@ -14,6 +14,8 @@ Shims:
     ``.Kmin_argKmin``).  pykeops 2.2.3 is the pinned third-party dependency; its source is not in
     /root/reference, so exact tie behaviour at d^2 == rc^2 is parity-unpinned by the reference.
   * ``numpy.NaN`` alias (utils/neighbors.py:21; removed in numpy 2).
+  * ``pymatgen.core.Lattice`` / ``Structure``: imported at utils/structure_utils.py:6 for ``create_structure``,
+    which nothing on this path calls.
 
 Nothing in the product package imports this file.
 """
@@ -84,6 +86,14 @@ def install_shims() -> None:
         pk.torch = pkt
         sys.modules["pykeops"] = pk
         sys.modules["pykeops.torch"] = pkt
+    if "pymatgen" not in sys.modules:  # utils/structure_utils.py:6 (create_structure only; never called here)
+        pm = types.ModuleType("pymatgen")
+        pmc = types.ModuleType("pymatgen.core")
+        pmc.Lattice = object
+        pmc.Structure = object
+        pm.core = pmc
+        sys.modules["pymatgen"] = pm
+        sys.modules["pymatgen.core"] = pmc
     if REFERENCE_SRC not in sys.path:
         sys.path.insert(0, REFERENCE_SRC)
 

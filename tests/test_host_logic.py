@@ -104,8 +104,13 @@ def test_sampling_parameters_mirror_the_reference_defaults():
     loaded = load_sampling_parameters(dict(algorithm="predictor_corrector", **{
         k: v for k, v in dataclasses.asdict(p).items() if k not in ("algorithm",)}))
     assert loaded == p
-    with pytest.raises(AssertionError):
+    adaptive = load_sampling_parameters(dict(algorithm="adaptive_corrector", **{
+        k: v for k, v in dataclasses.asdict(p).items() if k not in ("algorithm",)}))
+    assert adaptive.algorithm == "adaptive_corrector"
+    with pytest.raises(NotImplementedError):  # ODE / SDE solvers are outside the accelerated path
         load_sampling_parameters(dict(algorithm="ode"))
+    with pytest.raises(AssertionError):
+        load_sampling_parameters(dict(algorithm="euler"))
 
 
 def test_generator_plumbing_without_a_device():
