@@ -97,6 +97,62 @@ __global__ void pair_distances_fill_kernel(const float* __restrict__ positions, 
   }
 }
 
+// ---- repulsive pseudo-force of ForceFieldAugmentedScoreNetwork --------------------------------------------------
+// models/score_networks/force_field_augmented_score_network.py:44-236:
+//   cell = diag(clip(L[:3], min_box_size)); p = x @ cell; for every edge (i -> image of j) with 0 < d2 <= r0^2:
+//   disp = (p_j - p_i) + shift, r = |disp|, F_i += 2 s (r - r0) / (r + 1e-8) disp; out = [add_to +] F @ inverse(cell).
+// The reference builds the per-image adjacency (3 KeOps reductions + nonzero), gathers, and scatter_adds one Cartesian
+// component at a time; here one warp owns a source atom of a structure staged in shared memory and accumulates its
+// force in registers over the 27 images -- no edge list exists.
+__global__ void repulsive_pseudo_force_kernel(const float* __restrict__ x_rel, const float* __restrict__ lattice,
+                                              float min_box, float rc, float rc2, float strength, int32_t N,
+                                              const float* __restrict__ add_to, float* __restrict__ out,
+                                              int32_t* __restrict__ status) {
+  extern __shared__ float smem[];
+  float* px = smem; float* py = px + N; float* pz = py + N;
+  float* lat = pz + N;  // [27][3]
+  __shared__ float s_cell[9];
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x < 9) {
+    const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+    s_cell[threadIdx.x] = (r == c) ? fmaxf(lattice[b * 6 + r], min_box) : 0.0f;   // basis_transformations.py:253-256
+  }
+  __syncthreads();
+  stage_structure_with_cell(x_rel + b * N * 3, 1, N, px, py, pz, lat, s_cell);
+  if (threadIdx.x == 0 && !(shortest_cell_crossing_distance(s_cell) > rc))
+    atomicOr(status, (int)B200MD_STATUS_CUTOFF_TOO_LARGE);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < N; i += nwarps) {
+    const float xi = px[i], yi = py[i], zi = pz[i];
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    for (int img = 0; img < 27; ++img) {
+      const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
+      for (int j = lane; j < N; j += 32) {
+        float d2;
+        if (image_hit(xi, yi, zi, px[j], py[j], pz[j], lx, ly, lz, rc2, d2)) {
+          const float dx = (px[j] - xi) + lx, dy = (py[j] - yi) + ly, dz = (pz[j] - zi) + lz;   // :150-154
+          const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+          const float pref = 2.0f * strength * (r - rc) / (r + 1.0e-8f);                       // :104-108
+          fx += pref * dx; fy += pref * dy; fz += pref * dz;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      fx += __shfl_down_sync(0xffffffffu, fx, o);
+      fy += __shfl_down_sync(0xffffffffu, fy, o);
+      fz += __shfl_down_sync(0xffffffffu, fz, o);
+    }
+    if (lane == 0) {
+      const int64_t o3 = (b * N + i) * 3;
+      // relative force = F @ inverse(cell): the cell is diagonal here (reference: "Only orthogonal boxes")
+      float rx = fx / s_cell[0], ry = fy / s_cell[4], rz = fz / s_cell[8];
+      if (add_to) { rx += add_to[o3]; ry += add_to[o3 + 1]; rz += add_to[o3 + 2]; }
+      out[o3] = rx; out[o3 + 1] = ry; out[o3 + 2] = rz;
+    }
+  }
+}
+
 }  // namespace b200md
 
 using namespace b200md;
@@ -135,6 +191,23 @@ int b200md_pair_distances_fill(const float* positions, const float* cell, int32_
     cudaFuncSetAttribute(pair_distances_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); pair_distances_fill_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
       positions, cell, positions_are_relative, max_distance, n_atoms, offsets, distances_out); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_repulsive_pseudo_force(const float* x_rel, const float* lattice, float min_box_size, float radial_cutoff,
+                                  float strength, int64_t n_samples, int32_t n_atoms, const float* add_to_or_null,
+                                  float* out, int32_t* status, b200md_stream_t stream) {
+  if (!x_rel || !lattice || !out || !status || n_samples < 0 || n_atoms <= 0 || !(radial_cutoff > 0.f) || !(strength > 0.f))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_atoms > 4096) return B200MD_ERR_UNSUPPORTED;
+  if (n_samples == 0) return B200MD_OK;
+  const int threads = n_atoms >= 256 ? 256 : (n_atoms >= 64 ? 128 : 64);
+  const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(repulsive_pseudo_force_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); repulsive_pseudo_force_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+      x_rel, lattice, min_box_size, radial_cutoff, radial_cutoff * radial_cutoff, strength, n_atoms, add_to_or_null, out, status); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }

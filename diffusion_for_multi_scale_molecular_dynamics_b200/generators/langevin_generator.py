@@ -136,7 +136,7 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
     def _raise_on_status(self) -> None:
         if self._status is not None:
             _cabi.raise_on_status(self._status, AssertionError)
-        if isinstance(self.axl_network, ScoreNetwork):
+        if hasattr(self.axl_network, "raise_on_device_status"):
             self.axl_network.raise_on_device_status()
 
     def _begin_trajectory(self, device: torch.device) -> None:
@@ -310,7 +310,7 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
 
     # ---- predictor / corrector -----------------------------------------------------------------------------------
     def _defer_network_checks(self, defer: bool) -> None:
-        if isinstance(self.axl_network, ScoreNetwork):
+        if hasattr(self.axl_network, "defer_status_check"):
             self.axl_network.defer_status_check = defer
 
     def predictor_step(self, composition_i: AXL, index_i: int, cartesian_forces: torch.Tensor) -> AXL:

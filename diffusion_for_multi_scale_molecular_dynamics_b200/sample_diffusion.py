@@ -12,8 +12,9 @@ The yaml needs the reference's ``noise`` and ``sampling`` blocks; the network ar
 hyper-parameters or, failing that, from a ``model: score_network:`` block of the yaml (as in the training configs).
 Under ``torchrun`` (one process per GPU) the samples are sharded across ranks and rank 0 writes the files.
 
-Not carried over: the LAMMPS energy oracle (``energies.pt``), the force-field augmentation and ORION reporting -- they
-are outside the accelerated path; an ``oracle`` / ``force_field`` block is reported and ignored.
+A ``force_field`` block wraps the network in ``ForceFieldAugmentedScoreNetwork`` as in the reference.  Not carried over:
+the LAMMPS energy oracle (``energies.pt``) and ORION reporting -- they are outside the accelerated path; an ``oracle``
+block is reported and ignored.
 """
 import argparse
 import dataclasses
@@ -36,6 +37,8 @@ from diffusion_for_multi_scale_molecular_dynamics_b200.generators.load_sampling_
 from diffusion_for_multi_scale_molecular_dynamics_b200.generators.sampling_constraint import read_sampling_constraint
 from diffusion_for_multi_scale_molecular_dynamics_b200.generators.trajectory_initializer import \
     instantiate_trajectory_initializer
+from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.force_field_augmented_score_network import (
+    ForceFieldAugmentedScoreNetwork, ForceFieldParameters)
 from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.score_network import ScoreNetwork
 from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.score_network_factory import (
     SCORE_NETWORK_PARAMETERS_BY_ARCH, create_score_network, create_score_network_parameters)
@@ -235,12 +238,13 @@ def main(args: Optional[Any] = None, axl_network: Optional[ScoreNetwork] = None)
 
     hyper_params = load_and_backup_hyperparameters(config_file_path=args.config, output_directory=args.output)
     noise_parameters, sampling_parameters = extract_and_validate_parameters(hyper_params)
-    if "force_field" in hyper_params:
-        logger.warning("A force_field block is configured; the force-field augmentation is outside this sampling path "
-                       "and is ignored.")
     if axl_network is None:
         axl_network = get_axl_network(args.checkpoint, hyper_params)
     axl_network = axl_network.to(device)
+    if "force_field" in hyper_params:  # reference :132-139
+        force_field_parameters = ForceFieldParameters(**hyper_params["force_field"])
+        logger.info("Augmenting the AXL_network with an excluding Force Field.")
+        axl_network = ForceFieldAugmentedScoreNetwork(axl_network, force_field_parameters)
 
     trajectory_initializer = instantiate_trajectory_initializer(
         sampling_parameters=sampling_parameters,

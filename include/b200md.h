@@ -260,6 +260,19 @@ int b200md_pair_distances_fill(const float* positions, const float* cell,
                                b200md_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ForceFieldAugmentedScoreNetwork.get_relative_coordinates_pseudo_force
+ * (models/score_networks/force_field_augmented_score_network.py:44-236): repulsion phi(r) = s (r - r0)^2 for r < r0.
+ *   cell = diag(clip(lattice[:, :3], min_box_size)); p = x @ cell; for every (i, image of j) with 0 < d2 <= r0^2:
+ *   disp = (p_j - p_i) + shift;  F_i += 2 s (|disp| - r0) / (|disp| + 1e-8) disp;  out = [add_to +] F @ inverse(cell)
+ * x_rel [B,N,3], lattice [B,6], out [B,N,3] (relative-coordinate pseudo force, optionally added to a score).
+ * Sets B200MD_STATUS_CUTOFF_TOO_LARGE like get_periodic_adjacency_information (utils/neighbors.py:107-113).
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_repulsive_pseudo_force(const float* x_rel, const float* lattice, float min_box_size,
+                                  float radial_cutoff, float strength, int64_t n_samples, int32_t n_atoms,
+                                  const float* add_to_or_null, float* out, int32_t* status,
+                                  b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * EGNN score network: EGNNScoreNetwork._forward_unchecked (models/score_networks/egnn_score_network.py:226-303)
  * + EGNN / E_GCL (models/egnn.py:266-288,362-385) + the MASK-logit rule of ScoreNetwork.forward
  * (models/score_networks/score_network.py:183-185,221).

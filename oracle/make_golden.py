@@ -371,6 +371,37 @@ def golden_adaptive_corrector():
     save("adaptive_corrector", **out)
 
 
+def golden_force_field():
+    """ForceFieldAugmentedScoreNetwork (models/score_networks/force_field_augmented_score_network.py) of the reference:
+    the relative-coordinate pseudo force alone and on top of an EGNN score."""
+    from diffusion_for_multi_scale_molecular_dynamics.models.score_networks.force_field_augmented_score_network import (
+        ForceFieldAugmentedScoreNetwork, ForceFieldParameters)
+    out = {}
+    net = make_network("radial_sige", seed=320)
+    torch.manual_seed(420)
+    B, N = 4, 16
+    x = torch.rand(B, N, 3)
+    x[0, 1] = x[0, 0] + torch.tensor([0.01, 0.0, 0.0])  # a nearly coincident pair: large repulsion
+    x[1, 3] = x[1, 2]                                    # exactly coincident atoms: d2 == 0 to the home image
+    a = torch.randint(0, 3, (B, N))
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = torch.tensor([[7.0, 7.0, 7.0], [6.5, 7.5, 8.0], [7.2, 6.8, 7.0], [9.0, 7.0, 6.6]])
+    sigma = torch.rand(B, 1) * 0.3 + 0.01
+    batch = {NOISY_AXL_COMPOSITION: AXL(A=a, X=x, L=lattice), TIME: torch.rand(B, 1), NOISE: sigma,
+             CARTESIAN_FORCES: torch.zeros(B, N, 3)}
+    for rc, strength in ((1.5, 1.0), (2.5, 0.3)):
+        ff = ForceFieldAugmentedScoreNetwork(net, ForceFieldParameters(radial_cutoff=rc, strength=strength))
+        with torch.no_grad():
+            out[f"rc{rc}.force"] = ff.get_relative_coordinates_pseudo_force(batch)
+            augmented = ff(batch, conditional=False)
+        out[f"rc{rc}.augmented_x"], out[f"rc{rc}.augmented_a"] = augmented.X, augmented.A
+        out[f"rc{rc}.strength"] = strength
+    for key, value in net.state_dict().items():
+        out[f"sd.{key}"] = value
+    out["x"], out["a"], out["l"], out["sigma"] = x, a, lattice, sigma
+    save("force_field", **out)
+
+
 def golden_checkpoint():
     """A checkpoint shaped like the reference's Lightning checkpoints: ``state_dict`` keys under ``axl_network.`` and the
     reference's own parameter dataclass pickled (by class name) inside ``hyper_parameters``."""
@@ -387,7 +418,7 @@ def golden_checkpoint():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     ALL = [golden_noise_tables, golden_wrap_and_score, golden_neighbors, golden_segment, golden_egnn, golden_atom_types,
-           golden_trajectories, golden_analytical, golden_checkpoint, golden_pair_distances, golden_adaptive_corrector]
+           golden_trajectories, golden_analytical, golden_checkpoint, golden_pair_distances, golden_adaptive_corrector, golden_force_field]
     wanted = sys.argv[1:]   # e.g. `python oracle/make_golden.py pair_distances`; no argument = everything
     for fn in ALL:
         if not wanted or fn.__name__.replace("golden_", "") in wanted:

@@ -227,6 +227,25 @@ def compute_distances_in_batch(cartesian_positions: torch.Tensor, unit_cell: tor
     return distances[torch.logical_and(distances > 0.0, distances <= rc)]  # :113-121
 
 
+def repulsive_pseudo_force(x_rel: torch.Tensor, lattice: torch.Tensor, radial_cutoff: float, strength: float,
+                           min_box_size: float = 1.0) -> torch.Tensor:
+    """ForceFieldAugmentedScoreNetwork.get_relative_coordinates_pseudo_force
+    (models/score_networks/force_field_augmented_score_network.py:120-236), dense semantics."""
+    B, N, _ = x_rel.shape
+    lengths = lattice.clip(min=min_box_size)[:, :3]          # basis_transformations.py:253-256
+    basis = torch.diag_embed(lengths)
+    cart = torch.matmul(x_rel, basis)
+    adjacency, shifts, edge_batch, _ = periodic_adjacency(cart, basis, radial_cutoff)
+    src, dst = adjacency
+    displacements = cart[edge_batch, dst] - cart[edge_batch, src] + shifts           # :150-154
+    r = torch.linalg.norm(displacements, dim=1)
+    prefactors = 2.0 * strength * (r - radial_cutoff) / (r + torch.tensor(1.0e-8))  # :104-108
+    contributions = prefactors[:, None] * displacements
+    forces = torch.zeros(B * N, 3)
+    forces.index_add_(0, N * edge_batch + src, contributions)                        # :183-199
+    return torch.matmul(forces.reshape(B, N, 3), torch.inverse(basis))              # :226-234
+
+
 def periodic_pair_mask(relative_coordinates: torch.Tensor, unit_cell: torch.Tensor, radial_cutoff: float):
     """[B,N,N] bool: at least one of the 27 images of j lies within the cutoff of i (vectorised, for big cases)."""
     cart = torch.stack([_fp32_chain_matmul3(relative_coordinates[b], unit_cell[b])
