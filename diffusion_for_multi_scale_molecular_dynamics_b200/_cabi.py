@@ -147,6 +147,8 @@ SIGNATURES = {
     "b200md_pair_distances_count": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, _P, _P, _P]),
     "b200md_pair_distances_fill": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, _P, _P, _P]),
     "b200md_repulsive_pseudo_force": (c_int32, [_P, _P, c_float, c_float, c_float, c_int64, c_int32, _P, _P, _P, _P]),
+    "b200md_stillinger_weber_energy": (
+        c_int32, [_P, _P, _P, _P, c_int32, c_float, c_float, c_int64, c_int32, _P, _P, _P]),
     "b200md_egnn_param_count": (c_int32, [_CFG]),
     "b200md_egnn_packed_floats": (c_int64, [_CFG]),
     "b200md_egnn_pack_weights": (c_int32, [_CFG, POINTER(c_void_p), c_int32, _P, _P]),

@@ -153,6 +153,118 @@ __global__ void repulsive_pseudo_force_kernel(const float* __restrict__ x_rel, c
   }
 }
 
+// ---- Stillinger-Weber potential energy --------------------------------------------------------------------------
+// The reference evaluates sample energies by running LAMMPS (`pair_style sw`) one structure at a time
+// (oracle/lammps_energy_oracle.py:60-193); the energies feed its energy Kolmogorov-Smirnov metric.  Same functional
+// form here (LAMMPS pair_sw, Stillinger & Weber, PRB 31, 5262 (1985)), one CTA per structure:
+//   E = sum_{i<j} phi2(r_ij) + sum_i sum_{j<k} phi3(r_ij, r_ik, theta_jik)
+//   phi2 = A eps [B (sigma/r)^p - (sigma/r)^q] exp(sigma / (r - a sigma))                      entry (i, j, j)
+//   phi3 = lambda eps (cos theta - cos theta0)^2 exp(gamma_ij sigma_ij / (r_ij - a_ij sigma_ij))
+//                                                exp(gamma_ik sigma_ik / (r_ik - a_ik sigma_ik))    entries (i,j,k),(i,j,j),(i,k,k)
+// A warp owns a centre atom: it compacts the neighbours inside the pair cutoffs over the 27 images into a shared-memory
+// list (ballot), then its lanes split the pair terms and the j < k triplets.
+constexpr int kSwMaxNeighbours = 96;
+constexpr int kSwEntryFloats = 10;   // cut, cutsq, sigma, sigma*gamma, lambda*eps, costheta0, c5, c6, p, q
+struct SwEntry { float cut, cutsq, sigma, sigma_gamma, lambda_epsilon, costheta, c5, c6, powerp, powerq; };
+
+__global__ void stillinger_weber_energy_kernel(const float* __restrict__ x_rel, const float* __restrict__ lattice,
+                                               const int64_t* __restrict__ atom_types, const float* __restrict__ params,
+                                               int32_t n_types, float max_cut, float min_box, int32_t N,
+                                               float* __restrict__ energies, int32_t* __restrict__ status) {
+  extern __shared__ float smem[];
+  float* px = smem; float* py = px + N; float* pz = py + N;
+  float* lat = pz + N;                                    // [27][3]
+  int* types = reinterpret_cast<int*>(lat + 81);          // [N]
+  float* lists = reinterpret_cast<float*>(types + N);     // per warp: dx, dy, dz, r [kSwMaxNeighbours] + type
+  __shared__ float s_cell[9];
+  __shared__ double s_energy;
+  __shared__ int s_skip;
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x < 9) {
+    const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+    s_cell[threadIdx.x] = (r == c) ? lattice[b * 6 + r] : 0.0f;
+  }
+  if (threadIdx.x == 0) { s_energy = 0.0; s_skip = 0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float shortest = fminf(s_cell[0], fminf(s_cell[4], s_cell[8]));
+    if (shortest < min_box) s_skip = 1;   // "Got a box with a side length smaller than 3.0 Angstrom": energy 0 (:121-127)
+    else if (!(shortest > max_cut)) atomicOr(status, (int)B200MD_STATUS_CUTOFF_TOO_LARGE);
+  }
+  stage_structure_with_cell(x_rel + b * N * 3, 1, N, px, py, pz, lat, s_cell);
+  bool bad_type = false;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int64_t t = atom_types[b * N + i];
+    bad_type |= (t < 0 || t >= n_types);
+    types[i] = (int)(t < 0 ? 0 : (t >= n_types ? n_types - 1 : t));
+  }
+  if (bad_type) atomicOr(status, (int)B200MD_STATUS_A_OUT_OF_RANGE);
+  __syncthreads();
+  if (s_skip) { if (threadIdx.x == 0) energies[b] = 0.0f; return; }
+  const SwEntry* table = reinterpret_cast<const SwEntry*>(params);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float* ndx = lists + (size_t)warp * 5 * kSwMaxNeighbours;
+  float* ndy = ndx + kSwMaxNeighbours; float* ndz = ndy + kSwMaxNeighbours; float* nr = ndz + kSwMaxNeighbours;
+  int* nt = reinterpret_cast<int*>(nr + kSwMaxNeighbours);
+  float local = 0.f;
+  for (int i = warp; i < N; i += nwarps) {
+    const float xi = px[i], yi = py[i], zi = pz[i];
+    const int ti = types[i];
+    int cnt = 0;
+    for (int img = 0; img < 27; ++img) {
+      const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        float dx = 0.f, dy = 0.f, dz = 0.f, d2 = 0.f;
+        int tj = 0;
+        if (j < N) {
+          tj = types[j];
+          dx = (px[j] + lx) - xi; dy = (py[j] + ly) - yi; dz = (pz[j] + lz) - zi;
+          d2 = dx * dx + dy * dy + dz * dz;
+          hit = (d2 > 0.f) && (d2 < table[(ti * n_types + tj) * n_types + tj].cutsq);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int k = cnt + __popc(ballot & lt_mask);
+          if (k < kSwMaxNeighbours) { ndx[k] = dx; ndy[k] = dy; ndz[k] = dz; nr[k] = sqrtf(d2); nt[k] = tj; }
+        }
+        cnt += __popc(ballot);
+      }
+    }
+    if (cnt > kSwMaxNeighbours) { if (lane == 0) atomicOr(status, (int)B200MD_STATUS_EDGE_OVERFLOW); cnt = kSwMaxNeighbours; }
+    __syncwarp();
+    for (int k = lane; k < cnt; k += 32) {   // pair terms, half to each end
+      const SwEntry e = table[(ti * n_types + nt[k]) * n_types + nt[k]];
+      const float r = nr[k];
+      const float rp = (e.powerp == 4.0f) ? 1.0f / ((r * r) * (r * r)) : powf(r, -e.powerp);
+      const float rq = (e.powerq == 0.0f) ? 1.0f : powf(r, -e.powerq);
+      local += 0.5f * (e.c5 * rp - e.c6 * rq) * expf(e.sigma / (r - e.cut));
+    }
+    for (int ja = 0; ja < cnt; ++ja) {       // triplets centred on i
+      const int ta = nt[ja];
+      const SwEntry eij = table[(ti * n_types + ta) * n_types + ta];
+      const float r1 = nr[ja], ax = ndx[ja], ay = ndy[ja], az = ndz[ja];
+      const float exp1 = expf(eij.sigma_gamma / (r1 - eij.cut));
+      for (int kb = ja + 1 + lane; kb < cnt; kb += 32) {
+        const int tb = nt[kb];
+        const SwEntry eik = table[(ti * n_types + tb) * n_types + tb];
+        const SwEntry eijk = table[(ti * n_types + ta) * n_types + tb];
+        const float r2 = nr[kb];
+        const float cs = (ax * ndx[kb] + ay * ndy[kb] + az * ndz[kb]) / (r1 * r2);
+        const float delcs = cs - eijk.costheta;
+        local += eijk.lambda_epsilon * exp1 * expf(eik.sigma_gamma / (r2 - eik.cut)) * delcs * delcs;
+      }
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if (lane == 0) atomicAdd(&s_energy, (double)local);
+  __syncthreads();
+  if (threadIdx.x == 0) energies[b] = (float)s_energy;
+}
+
 }  // namespace b200md
 
 using namespace b200md;
@@ -208,6 +320,27 @@ int b200md_repulsive_pseudo_force(const float* x_rel, const float* lattice, floa
     cudaFuncSetAttribute(repulsive_pseudo_force_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); repulsive_pseudo_force_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
       x_rel, lattice, min_box_size, radial_cutoff, radial_cutoff * radial_cutoff, strength, n_atoms, add_to_or_null, out, status); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_stillinger_weber_energy(const float* x_rel, const float* lattice, const int64_t* atom_types,
+                                   const float* params, int32_t n_types, float max_cutoff, float min_box_size,
+                                   int64_t n_samples, int32_t n_atoms, float* energies_out, int32_t* status,
+                                   b200md_stream_t stream) {
+  if (!x_rel || !lattice || !atom_types || !params || !energies_out || !status || n_samples < 0 || n_atoms <= 0 ||
+      n_types <= 0 || !(max_cutoff > 0.f))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_atoms > 4096) return B200MD_ERR_UNSUPPORTED;
+  if (n_samples == 0) return B200MD_OK;
+  const int threads = n_atoms >= 256 ? 256 : 128;
+  const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float) + (size_t)n_atoms * sizeof(int) +
+                      (size_t)(threads / 32) * 5 * kSwMaxNeighbours * sizeof(float);
+  if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(stillinger_weber_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); stillinger_weber_energy_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
+      x_rel, lattice, atom_types, params, n_types, max_cutoff, min_box_size, n_atoms, energies_out, status); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }

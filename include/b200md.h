@@ -273,6 +273,23 @@ int b200md_repulsive_pseudo_force(const float* x_rel, const float* lattice, floa
                                   b200md_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stillinger-Weber potential energy of every structure of a batch: what the reference obtains from LAMMPS
+ * (`pair_style sw`, oracle/lammps_energy_oracle.py:60-193) one structure at a time, for its energy
+ * Kolmogorov-Smirnov metric (models/axl_diffusion_lightning_model.py:141,560-640).
+ *   E = sum_{i<j} phi2(r_ij) + sum_i sum_{j<k} phi3(r_ij, r_ik, theta_jik)       (LAMMPS pair_sw)
+ * x_rel [B,N,3], lattice [B,6] (orthogonal box diag(lattice[:, :3])), atom_types [B,N] int64 in [0, n_types).
+ * params [n_types^3][10] f32, entry (i,j,k) = { a*sigma, (a*sigma)^2, sigma, sigma*gamma, lambda*epsilon, costheta0,
+ * A*epsilon*B*sigma^p, A*epsilon*sigma^q, p, q }; pair terms use entry (i,j,j).  max_cutoff = largest a*sigma.
+ * A box side below min_box_size gives energy 0 (the reference skips such boxes, :121-127); a side not larger
+ * than max_cutoff raises B200MD_STATUS_CUTOFF_TOO_LARGE (neighbours beyond the first image shell).
+ * energies_out [B] f32 (eV).
+ * ---------------------------------------------------------------------------------------------- */
+int b200md_stillinger_weber_energy(const float* x_rel, const float* lattice, const int64_t* atom_types,
+                                   const float* params, int32_t n_types, float max_cutoff,
+                                   float min_box_size, int64_t n_samples, int32_t n_atoms,
+                                   float* energies_out, int32_t* status, b200md_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * EGNN score network: EGNNScoreNetwork._forward_unchecked (models/score_networks/egnn_score_network.py:226-303)
  * + EGNN / E_GCL (models/egnn.py:266-288,362-385) + the MASK-logit rule of ScoreNetwork.forward
  * (models/score_networks/score_network.py:183-185,221).
