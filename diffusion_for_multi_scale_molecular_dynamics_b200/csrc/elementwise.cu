@@ -66,6 +66,14 @@ __global__ void wrap_kernel(const float* x, float* out, int64_t n) {
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = wrap_unit(x[i]);
 }
+// same, four values per thread with 128-bit accesses (n % 4 == 0, 16-byte aligned pointers)
+__global__ void wrap_kernel_v4(const float4* x, float4* out, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    out[i] = make_float4(wrap_unit(v.x), wrap_unit(v.y), wrap_unit(v.z), wrap_unit(v.w));
+  }
+}
 
 // -------------------------------------------------------------------------------------------------
 // Coordinate update, generators/langevin_generator.py:194-200:
@@ -104,6 +112,47 @@ __global__ void pc_coordinates_update_kernel(const float* x, const float* __rest
     for (int d = 0; d < D; ++d) { xv[d] = x[t * D + d]; sv[d] = s[t * D + d]; }
 #pragma unroll
     for (int d = 0; d < D; ++d) out[t * D + d] = pc_update_value(xv[d], sv[d], zz[d], sw, sigma, nw);
+  }
+}
+
+// D = 3, four atoms (twelve consecutive floats = three float4) per thread: every access is a full 128-bit vector, so
+// the kernel streams at HBM speed instead of issuing stride-3 scalar loads.  Same arithmetic and the same Philox
+// counters (one block per (sample, atom)) as pc_coordinates_update_kernel<3>; needs (n_samples * n_atoms) % 4 == 0.
+__global__ void pc_coordinates_update_v4_kernel(const float4* x, const float4* __restrict__ s,
+                                                const float4* __restrict__ z, float sw, float sigma, float nw,
+                                                int64_t n_groups, int32_t n_atoms, uint64_t seed, uint32_t step_id,
+                                                uint64_t sample_offset, float4* out) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    float xv[12], sv[12], zv[12];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 a = x[g * 3 + k], b = s[g * 3 + k];
+      xv[4 * k] = a.x; xv[4 * k + 1] = a.y; xv[4 * k + 2] = a.z; xv[4 * k + 3] = a.w;
+      sv[4 * k] = b.x; sv[4 * k + 1] = b.y; sv[4 * k + 2] = b.z; sv[4 * k + 3] = b.w;
+    }
+    if (z != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 c = z[g * 3 + k];
+        zv[4 * k] = c.x; zv[4 * k + 1] = c.y; zv[4 * k + 2] = c.z; zv[4 * k + 3] = c.w;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int64_t t = g * 4 + a;
+        const int64_t smp = t / n_atoms;
+        const int32_t atom = (int32_t)(t - smp * n_atoms);
+        float zz[4];
+        normal4(draw_block(seed, sample_offset + (uint64_t)smp, (uint32_t)atom, step_id, B200MD_DRAW_COORD_NORMAL), zz);
+        zv[3 * a] = zz[0]; zv[3 * a + 1] = zz[1]; zv[3 * a + 2] = zz[2];
+      }
+    }
+    float r[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r[k] = pc_update_value(xv[k], sv[k], zv[k], sw, sigma, nw);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[g * 3 + k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
   }
 }
 
@@ -553,7 +602,13 @@ int b200md_draw_gumbel(float* out, int64_t n_samples, int32_t units, int32_t uni
 int b200md_wrap_to_unit_cell(const float* x, float* out, int64_t n, b200md_stream_t stream) {
   if (n < 0 || (n > 0 && (!x || !out))) return B200MD_ERR_INVALID_ARGUMENT;
   if (n == 0) return B200MD_OK;
-  { ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream)); wrap_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, out, n); }
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream));
+    wrap_kernel_v4<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), n / 4);
+  } else {
+    ProfileScope ps__(B200MD_KERNEL_OTHER, as_stream(stream));
+    wrap_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
+  }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }
@@ -568,7 +623,14 @@ int b200md_pc_coordinates_update(const float* x, const float* s, const float* z,
   const int64_t total = n_samples * n_atoms;
   const unsigned g = grid_for(total, 256);
   cudaStream_t st = as_stream(stream);
-  {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(z) |
+                         reinterpret_cast<uintptr_t>(x_out)) & 15u) == 0;
+  if (D == 3 && (total & 3) == 0 && aligned) {
+    ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
+    pc_coordinates_update_v4_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(z),
+        score_weight, sigma, noise_weight, total / 4, n_atoms, seed, step_id, sample_offset, reinterpret_cast<float4*>(x_out));
+  } else {
     ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
     switch (D) {
       case 1: pc_coordinates_update_kernel<1><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
