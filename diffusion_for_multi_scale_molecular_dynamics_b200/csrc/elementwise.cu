@@ -617,9 +617,9 @@ int b200md_pc_coordinates_update(const float* x, const float* s, const float* z,
                                  float sigma, float noise_weight, int64_t n_samples, int32_t n_atoms,
                                  int32_t D, uint64_t seed, uint32_t step_id, uint64_t sample_offset,
                                  float* x_out, b200md_stream_t stream) {
+  if (n_samples == 0) return B200MD_OK;
   if (!x || !s || !x_out || n_samples < 0 || n_atoms <= 0 || D < 1 || D > 3)
     return B200MD_ERR_INVALID_ARGUMENT;
-  if (n_samples == 0) return B200MD_OK;
   const int64_t total = n_samples * n_atoms;
   const unsigned g = grid_for(total, 256);
   cudaStream_t st = as_stream(stream);

@@ -274,10 +274,10 @@ extern "C" {
 int b200md_pair_distances_count(const float* positions, const float* cell, int32_t positions_are_relative,
                                 float max_distance, int64_t n_samples, int32_t n_atoms, int32_t* counts,
                                 int64_t* distances_per_structure, b200md_stream_t stream) {
+  if (n_samples == 0) return B200MD_OK;
   if (!positions || !cell || !counts || !distances_per_structure || n_samples < 0 || n_atoms <= 0 || !(max_distance > 0.f))
     return B200MD_ERR_INVALID_ARGUMENT;
   if (n_atoms > 4096) return B200MD_ERR_UNSUPPORTED;
-  if (n_samples == 0) return B200MD_OK;
   const int threads = n_atoms >= 256 ? 256 : (n_atoms >= 64 ? 128 : 64);
   const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float);
   if (smem > 48 * 1024)
@@ -291,10 +291,10 @@ int b200md_pair_distances_count(const float* positions, const float* cell, int32
 int b200md_pair_distances_fill(const float* positions, const float* cell, int32_t positions_are_relative,
                                float max_distance, int64_t n_samples, int32_t n_atoms, const int64_t* offsets,
                                float* distances_out, b200md_stream_t stream) {
+  if (n_samples == 0) return B200MD_OK;
   if (!positions || !cell || !offsets || !distances_out || n_samples < 0 || n_atoms <= 0 || !(max_distance > 0.f))
     return B200MD_ERR_INVALID_ARGUMENT;
   if (n_atoms > 4096) return B200MD_ERR_UNSUPPORTED;
-  if (n_samples == 0) return B200MD_OK;
   int threads = n_atoms >= 256 ? 256 : (n_atoms >= 64 ? 128 : 64);
   if (n_atoms > 512) threads = 128;
   const size_t smem = (size_t)(3 * n_atoms + 81) * sizeof(float) + (size_t)(threads / 32) * 3 * n_atoms * sizeof(float);

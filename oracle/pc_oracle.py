@@ -279,7 +279,7 @@ def edges_with_radial_cutoff(relative_coordinates, unit_cell, radial_cutoff: flo
 def fully_connected_edges(n_nodes: int, batch_size: int) -> torch.Tensor:
     """get_edges_batch (models/egnn_utils.py:73-104): order (b, x, y != x)."""
     pairs = [(x, y) for x in range(n_nodes) for y in range(n_nodes) if x != y]
-    base = torch.tensor(pairs, dtype=torch.int64)
+    base = torch.tensor(pairs, dtype=torch.int64).reshape(-1, 2)   # (0, 2) for a single atom
     return torch.cat([base + n_nodes * b for b in range(batch_size)])
 
 

@@ -1,0 +1,97 @@
+"""GPU edge cases of the path: empty and degenerate inputs, tile-boundary edge counts, and size-independent properties of
+the score network at the largest BASELINE supercell (4x4x4, 512 atoms), where the CPU oracle is too slow to run."""
+import pytest
+import torch
+
+from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.egnn_score_network import (
+    EGNNScoreNetwork, EGNNScoreNetworkParameters)
+from diffusion_for_multi_scale_molecular_dynamics_b200.utils.basis_transformations import \
+    map_relative_coordinates_to_unit_cell
+from diffusion_for_multi_scale_molecular_dynamics_b200.utils.structure_utils import compute_distances_in_batch
+from oracle import pc_oracle as oracle
+from tests.test_gpu_parity import PRODUCTION, SCORE_CANCELLATION_FLOOR, assert_rel, network_batch
+
+pytestmark = pytest.mark.gpu
+
+WIDE = dict(message_hidden_dimensions_size=64, coordinate_hidden_dimensions_size=64, node_hidden_dimensions_size=64,
+            message_n_hidden_dimensions=1, coordinate_n_hidden_dimensions=1, node_n_hidden_dimensions=1, n_layers=2)
+FULL = dict(residual=True, attention=False, normalize=False, tanh=False, coords_agg="mean", message_agg="mean")
+
+
+def forward_both(cuda_device, hp, a, x, lattice, sigma, impl=_cabi.IMPL_AUTO, seed=11):
+    torch.manual_seed(seed)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(cuda_device)
+    net.kernel_impl = impl
+    out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
+    logits, score = oracle.egnn_score_forward(sd, dict(FULL, **hp), a, x, lattice, sigma)
+    return net, out, logits, score
+
+
+@pytest.mark.parametrize("impl", [_cabi.IMPL_FFMA, _cabi.IMPL_TCGEN05_F16X3_TS], ids=["ffma", "f16x3ts"])
+@pytest.mark.parametrize("B,N,edges", [(64, 2, "fully_connected"), (3, 1, "fully_connected"), (5, 12, "radial_cutoff"),
+                                       (1, 40, "radial_cutoff")],
+                         ids=["128-edges-one-full-tile", "single-atom-no-edges", "sparse-some-isolated-atoms", "one-structure"])
+def test_egnn_degenerate_graphs(cuda_device, B, N, edges, impl):
+    """Exactly one full tile of 128 edges, no edge at all, isolated atoms (cutoff 1.2 A in a 9 A box), a single
+    structure: the tile loops, the segmented reductions and the mean aggregation (division by max(deg, 1))."""
+    hp = dict(num_atom_types=2, edges=edges, **WIDE)
+    if edges == "radial_cutoff":
+        hp["radial_cutoff"] = 1.2 if B == 5 else 3.0
+    torch.manual_seed(B * 100 + N)
+    x = torch.rand(B, N, 3)
+    a = torch.randint(0, 3, (B, N))
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = 9.0
+    sigma = torch.rand(B, 1) * 0.3 + 0.01
+    net, out, logits, score = forward_both(cuda_device, hp, a, x, lattice, sigma, impl)
+    assert_rel(out.A, logits, 1e-5, "logits")
+    assert_rel(out.X, score, 1e-5, "score", floor=SCORE_CANCELLATION_FLOOR)
+    if (B, N) == (64, 2):
+        assert net.last_number_of_edges() == 128
+    if N == 1:
+        assert net.last_number_of_edges() == 0
+
+
+def test_empty_batches(cuda_device):
+    """n_samples == 0 through the C ABI: nothing launched, empty outputs."""
+    empty = torch.empty(0, 8, 3, device=cuda_device)
+    assert map_relative_coordinates_to_unit_cell(empty).shape == (0, 8, 3)
+    cell = torch.empty(0, 3, 3, device=cuda_device)
+    assert compute_distances_in_batch(empty, cell, 2.0).shape == (0,)
+    out = torch.empty_like(empty)
+    assert _cabi.lib().b200md_pc_coordinates_update(_cabi.ptr(empty), _cabi.ptr(empty), None, 0.1, 0.1, 0.1, 0, 8, 3, 1, 1,
+                                                    0, _cabi.ptr(out), _cabi.stream_ptr(cuda_device)) == 0
+    assert _cabi.lib().b200md_pc_coordinates_update(None, None, None, 0.1, 0.1, 0.1, 4, 8, 3, 1, 1, 0, None,
+                                                    _cabi.stream_ptr(cuda_device)) != 0  # null pointers are refused
+
+
+def test_score_network_invariances_at_the_largest_supercell(cuda_device):
+    """Si 4x4x4 (512 atoms, ~45k edges per structure, production widths): the score is invariant under a rigid
+    translation of the structure (modulo the cell) and equivariant under a permutation of the atoms; the logits follow
+    the permutation.  Exact symmetries of the reference network (models/score_networks/test_score_network_equivariance)."""
+    hp = dict(num_atom_types=1, **PRODUCTION)
+    torch.manual_seed(21)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp)).to(cuda_device)
+    B, N, length = 4, 512, 21.72
+    x = torch.rand(B, N, 3)
+    a = torch.randint(0, 2, (B, N))
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = length
+    sigma = torch.full((B, 1), 0.1)
+    base = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
+    assert 40000 < net.last_number_of_edges() / B < 50000
+    shifted = torch.remainder(x + torch.tensor([0.31, 0.77, 0.05]), 1.0)
+    moved = net(network_batch(a, shifted, lattice, sigma, cuda_device), conditional=False)
+    scale = base.X.abs().max()
+    # S = z . Gamma . zhat is a difference of unit-size fp32 numbers: 2^-22 is the floor of any evaluation order
+    assert (moved.X - base.X).abs().max() <= 2e-4 * scale + SCORE_CANCELLATION_FLOOR
+    finite = torch.isfinite(base.A)
+    assert (moved.A[finite] - base.A[finite]).abs().max() <= 2e-4 * base.A[finite].abs().max()
+    perm = torch.randperm(N)
+    permuted = net(network_batch(a[:, perm], x[:, perm], lattice, sigma, cuda_device), conditional=False)
+    assert (permuted.X - base.X[:, perm.to(cuda_device)]).abs().max() <= 2e-5 * scale + SCORE_CANCELLATION_FLOOR
+    assert (permuted.A[finite[:, perm.to(cuda_device)]] - base.A[:, perm.to(cuda_device)][finite[:, perm.to(cuda_device)]]
+            ).abs().max() <= 2e-5 * base.A[finite].abs().max()
