@@ -6,14 +6,19 @@
 // launch, no per-edge tensor ever reaches HBM -- but every Linear(K -> N) of the chain runs on the tensor cores
 // (see tc_common.cuh for the pipeline and the two precision modes).
 //
-// One persistent CTA per SM, tile = 128 consecutive edges of the (src-sorted) edge list.  Warp roles:
+// Two kernels:
+//   egnn_edge_ts_kernel (egnn_edge_ts.cuh)   3xFP16, activations live in tensor memory (tcgen05.mma .ts): the production path;
+//   egnn_edge_tc_kernel<PREC> (below)         3xTF32 / 3xFP16 with the A operand staged in shared memory: the first
+//                                             tensor-core version, kept for widths that are only multiples of 32, for the
+//                                             fp32 exponent range, and for A/B runs.
+// egnn_edge_tc_kernel: one persistent CTA per SM, tile = 128 consecutive edges of the (src-sorted) edge list.  Warps:
 //   warp 0      bulk-copy producer of the weight chunks (L2-resident image -> 4-stage shared-memory ring);
-//   warp 1      TMEM allocator and single-thread MMA issuer;
-//   warps 2-9   "epilogue" warps: build the first activation from P[src] + Q[dst] + r w_r, and between two Linear
-//               layers read the accumulator (tcgen05.ld), add the bias, apply SiLU, split into hi/lo and write the
-//               next layer's A operand chunk by chunk, so that the MMA of layer g+1 on chunk c overlaps the epilogue
-//               of layer g on chunk c+1.  They also do the segmented warp reductions (messages -> agg, coordinate
-//               updates -> xagg) with one atomic per (segment, column).
+//   warp 1      TMEM allocator and MMA issuer (converged warp, elected lane);
+//   warps 2-17  "epilogue" warps (4 per TMEM lane quarter): build the first activation from P[src] + Q[dst] + r w_r, and
+//               between two Linear layers read the accumulator (tcgen05.ld), add the bias, apply SiLU, split into hi/lo
+//               and write the next layer's A operand chunk by chunk, so that the MMA of layer g+1 on chunk c overlaps
+//               the epilogue of layer g on chunk c+1.  They also do the segmented warp reductions (messages -> agg,
+//               coordinate updates -> xagg) with one atomic per (segment, column).
 #include <math_constants.h>
 
 #include "egnn.cuh"
