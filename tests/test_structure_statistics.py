@@ -89,3 +89,55 @@ def test_gpu_pair_distances_at_sampling_size(cuda_device):
     metric.register_predicted_samples(out[out.numel() // 2:])
     distance, _ = metric.compute_kolmogorov_smirnov_distance_and_pvalue()
     assert distance < 0.01  # two halves of the same uniform ensemble
+
+
+@pytest.mark.gpu
+def test_sampled_structures_match_the_data_distribution(cuda_device):
+    """The reference's validation loop in miniature (models/axl_diffusion_lightning_model.py:520-640): sample with the
+    analytical score network (a diamond crystal with Gaussian displacements sigma_d), then compare the samples with
+    structures drawn directly from that data distribution through the reference's two sample-quality statistics --
+    pair distances and Stillinger-Weber energies, each through KolmogorovSmirnovMetrics -- all computed on the GPU."""
+    from diffusion_for_multi_scale_molecular_dynamics_b200.generators.langevin_generator import LangevinGenerator
+    from diffusion_for_multi_scale_molecular_dynamics_b200.generators.predictor_corrector_axl_generator import \
+        PredictorCorrectorSamplingParameters
+    from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.analytical_score_network import (
+        AnalyticalScoreNetwork, AnalyticalScoreNetworkParameters)
+    from diffusion_for_multi_scale_molecular_dynamics_b200.namespace import AXL, AXL_COMPOSITION
+    from diffusion_for_multi_scale_molecular_dynamics_b200.noise_schedulers.noise_parameters import NoiseParameters
+    from diffusion_for_multi_scale_molecular_dynamics_b200.oracle.energy_oracle_factory import (
+        create_energy_oracle, create_energy_oracle_parameters)
+    diamond = [[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [.25, .25, .25], [.25, .75, .75], [.75, .25, .75],
+               [.75, .75, .25]]
+    sigma_d, B, T, length = 0.01, 1024, 200, 5.43
+    network = AnalyticalScoreNetwork(AnalyticalScoreNetworkParameters(
+        number_of_atoms=8, num_atom_types=1, kmax=4, equilibrium_relative_coordinates=diamond, sigma_d=sigma_d)).to(cuda_device)
+    sampling = PredictorCorrectorSamplingParameters(number_of_samples=B, number_of_atoms=8, num_atom_types=1,
+                                                    use_fixed_lattice_parameters=True, cell_dimensions=[length] * 3)
+    generator = LangevinGenerator(NoiseParameters(total_time_steps=T, sigma_min=0.001), sampling, network)
+    generator.seed = 23
+    samples = generator.sample(B, cuda_device)
+    torch.manual_seed(5)
+    data_x = torch.remainder(torch.tensor(diamond) + sigma_d * torch.randn(B, 8, 3), 1.0).to(cuda_device)
+    cell = get_orthogonal_basis_vectors(B, [length] * 3).to(cuda_device)
+    structure_metric = KolmogorovSmirnovMetrics()
+    structure_metric.register_reference_samples(compute_distances_in_batch(data_x * length, cell, 5.0))
+    structure_metric.register_predicted_samples(compute_distances_in_batch(samples.X * length, cell, 5.0))
+    distance, _ = structure_metric.compute_kolmogorov_smirnov_distance_and_pvalue()
+    assert distance < 0.02, f"structure KS distance {distance:.4f}"
+    energy_oracle = create_energy_oracle(create_energy_oracle_parameters(dict(name="lammps", sw_coeff_filename="Si.sw"), ["Si"]))
+    energy_metric = KolmogorovSmirnovMetrics()
+    energy_metric.register_reference_samples(energy_oracle.compute_oracle_energies(
+        {AXL_COMPOSITION: AXL(A=samples.A, X=data_x, L=samples.L)}))
+    energy_metric.register_predicted_samples(energy_oracle.compute_oracle_energies({AXL_COMPOSITION: samples}))
+    distance, _ = energy_metric.compute_kolmogorov_smirnov_distance_and_pvalue()
+    # the energy grows with the square of the displacement width, which the 200-step sampler reproduces to a few per
+    # cent (finite step, sigma_min): a visible but small shift of the energy distribution
+    assert distance < 0.2, f"energy KS distance {distance:.4f}"
+    # a deliberately wrong ensemble (twice the displacement width) is told apart by both statistics
+    wrong_x = torch.remainder(torch.tensor(diamond) + 2 * sigma_d * torch.randn(B, 8, 3), 1.0).to(cuda_device)
+    energy_metric.reset()
+    energy_metric.register_reference_samples(energy_oracle.compute_oracle_energies(
+        {AXL_COMPOSITION: AXL(A=samples.A, X=data_x, L=samples.L)}))
+    energy_metric.register_predicted_samples(energy_oracle.compute_oracle_energies(
+        {AXL_COMPOSITION: AXL(A=samples.A, X=wrong_x, L=samples.L)}))
+    assert energy_metric.compute_kolmogorov_smirnov_distance_and_pvalue()[0] > 0.5
