@@ -170,6 +170,10 @@ __global__ void egnn_graph_count_kernel(const float* __restrict__ x_rel, const f
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   int local = 0;
+  // minimum-image shortcut (graph.cuh): valid when the cutoff is below half of every box length, which the clipped
+  // EGNN box guarantees unless the cutoff assert above has fired
+  const float Lx = s_cell[0], Ly = s_cell[4], Lz = s_cell[8];
+  const bool min_image = !fully_connected && (2.0f * rc < fminf(Lx, fminf(Ly, Lz)));
   for (int i = warp; i < N; i += nwarps) {
     float xi = 0.f, yi = 0.f, zi = 0.f;
     if (!fully_connected) { xi = px[i]; yi = py[i]; zi = pz[i]; }
@@ -177,7 +181,10 @@ __global__ void egnn_graph_count_kernel(const float* __restrict__ x_rel, const f
     for (int w = 0; w < W; ++w) {
       const int j = w * 32 + lane;
       bool hit = false;
-      if (j < N) hit = fully_connected ? (j != i) : any_image_hit(xi, yi, zi, px[j], py[j], pz[j], lat, rc2);
+      if (j < N)
+        hit = fully_connected ? (j != i)
+                              : (min_image ? min_image_hit(xi, yi, zi, px[j], py[j], pz[j], Lx, Ly, Lz, rc2)
+                                           : any_image_hit(xi, yi, zi, px[j], py[j], pz[j], lat, rc2));
       const unsigned ballot = __ballot_sync(0xffffffffu, hit);
       if (lane == 0) bitmask[(b * N + i) * W + w] = ballot;
       d += __popc(ballot);

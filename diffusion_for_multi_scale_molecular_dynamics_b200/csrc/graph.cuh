@@ -30,6 +30,27 @@ __device__ __forceinline__ bool any_image_hit(float xi, float yi, float zi, floa
   return first_image_hit(xi, yi, zi, xj, yj, zj, lat, rc2) >= 0;
 }
 
+// Orthogonal cell with rc < L / 2 on every axis (the EGNN box: L' = max(L, 2.2 rc), egnn_score_network.py:236-240):
+// at most ONE periodic image of j can lie inside the cutoff of i, and it is the one that minimises |dx|, |dy|, |dz|
+// axis by axis.  With a diagonal cell the image vector is (n0 Lx, n1 Ly, n2 Lz) exactly, so d2(n) = fl(fl(a_n0 + b_n1) +
+// c_n2) with a_n = fl(fl(x_i - fl(x_j + n Lx))^2) depends on one image index per axis and is monotone in each term:
+// the minimum over the 27 images is reached at the per-axis minima, with the same rounding chain as the full sweep.
+// "Some image has 0 < d2 <= rc2" is then "0 < min d2 <= rc2": if the minimum is 0 (coincident atoms, or i == j) every
+// other image is at least L - |d| > rc away.  One test instead of 27 -- the pruning a cell list would give at larger
+// L / rc, obtained here from the minimum-image property.
+__device__ __forceinline__ float min_image_square(float xi, float xj, float L) {
+  const float dm = __fsub_rn(xi, __fadd_rn(xj, -L));
+  const float d0 = __fsub_rn(xi, __fadd_rn(xj, 0.0f));
+  const float dp = __fsub_rn(xi, __fadd_rn(xj, L));
+  return fminf(__fmul_rn(d0, d0), fminf(__fmul_rn(dm, dm), __fmul_rn(dp, dp)));
+}
+__device__ __forceinline__ bool min_image_hit(float xi, float yi, float zi, float xj, float yj, float zj, float Lx,
+                                              float Ly, float Lz, float rc2) {
+  const float d2 = __fadd_rn(__fadd_rn(min_image_square(xi, xj, Lx), min_image_square(yi, yj, Ly)),
+                             min_image_square(zi, zj, Lz));
+  return (d2 > 0.0f) && (d2 <= rc2);
+}
+
 // Shortest distance between opposite faces of the cell (utils/neighbors.py:310-351).
 __device__ __forceinline__ float shortest_cell_crossing_distance(const float* a) {
   const float c12x = a[1] * a[5] - a[2] * a[4], c12y = a[2] * a[3] - a[0] * a[5], c12z = a[0] * a[4] - a[1] * a[3];
