@@ -46,6 +46,7 @@ STATUS_MESSAGES = {
 
 DRAW_COORD_NORMAL, DRAW_GUMBEL, DRAW_BINARY, DRAW_LATTICE_NORMAL = 0, 1, 2, 3
 DRAW_INIT_UNIFORM, DRAW_REPAINT_NORMAL, DRAW_REPAINT_UNIFORM, DRAW_REPAINT_INIT = 4, 5, 6, 7
+DRAW_LATTICE_NORMAL_SECOND = 8  # the corrector's second lattice draw (reference langevin_generator.py:771-777)
 
 ATOM_GREEDY, ATOM_ONE_TRANSITION, ATOM_LAST_STEP = 1, 2, 4
 GRAPH_UNIQUE_PAIRS, GRAPH_PER_IMAGE = 0, 1

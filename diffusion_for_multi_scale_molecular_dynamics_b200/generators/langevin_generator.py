@@ -176,7 +176,9 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
                           _cabi.DRAW_COORD_NORMAL)
 
     def _draw_lattice_gaussian_sample(self, number_of_samples):
-        return self._draw("normal", number_of_samples, 0, self.num_lattice_parameters, _cabi.DRAW_LATTICE_NORMAL)
+        draw_id = _cabi.DRAW_LATTICE_NORMAL_SECOND if getattr(self, "_second_lattice_draw", False) \
+            else _cabi.DRAW_LATTICE_NORMAL
+        return self._draw("normal", number_of_samples, 0, self.num_lattice_parameters, draw_id)
 
     def _draw_gumbel_sample(self, number_of_samples):
         return self._draw("gumbel", number_of_samples, self.number_of_atoms, self.num_classes, _cabi.DRAW_GUMBEL)
@@ -405,8 +407,14 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
             eps_l = self._get_lattice_parameters_corrector_step_size(index_i, sigma_n_i, model_predictions_i.L,
                                                                      z_lattice)
             sqrt_2eps_l = torch.sqrt(2 * torch.as_tensor(eps_l, dtype=torch.float32))
-            corrected_lp_i = self._lattice_parameters_update(composition_i.L, model_predictions_i.L, sigma_n_i, eps_l,
-                                                             sqrt_2eps_l, z_lattice)
+            # As in the reference (:758-777) the update is NOT given z_lattice: that draw only feeds the step size (the
+            # adaptive corrector uses it) and the update draws its own noise -- a second, independent lattice draw.
+            self._second_lattice_draw = True
+            try:
+                corrected_lp_i = self._lattice_parameters_update(composition_i.L, model_predictions_i.L, sigma_n_i,
+                                                                 eps_l, sqrt_2eps_l)
+            finally:
+                self._second_lattice_draw = False
 
         if self.atom_type_transition_in_corrector:
             q, q_bar, q_bar_tm1 = (table[idx] for table in self._tables_on(device))

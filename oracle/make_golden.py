@@ -196,14 +196,15 @@ def golden_atom_types():
 class TapedHooks:
     """Patch the reference's noise draws with a NoiseTape (per-kind streams)."""
 
-    def __init__(self, generator, tape: NoiseTape):
+    def __init__(self, generator, tape: NoiseTape, lattice_noise: bool = False):
         g = generator
         B_of = lambda n: n  # noqa: E731
         self.patches = [
             mock.patch.object(g, "_draw_coordinates_gaussian_sample",
                               side_effect=lambda n: tape.normal("coordinates", B_of(n), g.number_of_atoms, 3)),
             mock.patch.object(g, "_draw_lattice_gaussian_sample",
-                              side_effect=lambda n: torch.zeros(n, g.num_lattice_parameters)),
+                              side_effect=(lambda n: tape.normal("lattice", n, g.num_lattice_parameters)) if lattice_noise
+                              else (lambda n: torch.zeros(n, g.num_lattice_parameters))),
             mock.patch.object(g, "_draw_gumbel_sample",
                               side_effect=lambda n: tape.gumbel(g.small_epsilon, n, g.number_of_atoms, g.num_classes)),
             mock.patch.object(g, "_draw_binary_sample", side_effect=lambda n: tape.uniform("binary", n, g.number_of_atoms)),
@@ -402,6 +403,38 @@ def golden_force_field():
     save("force_field", **out)
 
 
+def golden_free_lattice():
+    """LangevinGenerator with use_fixed_lattice_parameters=False: the lattice parameters diffuse too (the EGNN lattice
+    score is zero, so they move by the injected noise) and the radius graph follows the changing box."""
+    out = {}
+    variant, B, N, a, T, n_corr = "radial_sige", 3, 16, 7.0, 5, 1
+    net = make_network(variant, seed=330)
+    num_atom_types = EGNN_VARIANTS[variant]["num_atom_types"]
+    noise_parameters = NoiseParameters(total_time_steps=T, sigma_min=0.005, sigma_max=0.5)
+    sampling = PredictorCorrectorSamplingParameters(
+        number_of_samples=B, number_of_atoms=N, num_atom_types=num_atom_types, number_of_corrector_steps=n_corr,
+        use_fixed_lattice_parameters=False, cell_dimensions=[a, a, a])
+    gen = LangevinGenerator(noise_parameters, sampling, net)
+    torch.manual_seed(430)
+    x0 = torch.rand(B, N, 3)
+    a0 = torch.full((B, N), num_atom_types, dtype=torch.long)
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = torch.tensor([[7.0, 7.2, 6.9], [7.4, 7.0, 7.1], [6.8, 7.3, 7.0]])
+    with torch.no_grad(), TapedHooks(gen, NoiseTape(seed=80), lattice_noise=True):
+        final = gen.sample_from_noisy_composition(AXL(A=a0.clone(), X=x0.clone(), L=lattice.clone()), T, 0)
+    with torch.no_grad(), TapedHooks(gen, NoiseTape(seed=81), lattice_noise=True):
+        p = gen.predictor_step(AXL(A=a0.clone(), X=x0.clone(), L=lattice.clone()), 3, torch.zeros_like(x0))
+        c = gen.corrector_step(AXL(A=p.A.clone(), X=p.X.clone(), L=p.L.clone()), 2, torch.zeros_like(x0))
+    for key, value in net.state_dict().items():
+        out[f"sd.{key}"] = value
+    out["x0"], out["a0"], out["l"] = x0, a0, lattice
+    out["final_a"], out["final_x"], out["final_l"] = final.A, final.X, final.L
+    out["pred_a"], out["pred_x"], out["pred_l"] = p.A, p.X, p.L
+    out["corr_a"], out["corr_x"], out["corr_l"] = c.A, c.X, c.L
+    out["T"], out["n_corr"] = T, n_corr
+    save("free_lattice", **out)
+
+
 def golden_checkpoint():
     """A checkpoint shaped like the reference's Lightning checkpoints: ``state_dict`` keys under ``axl_network.`` and the
     reference's own parameter dataclass pickled (by class name) inside ``hyper_parameters``."""
@@ -418,7 +451,7 @@ def golden_checkpoint():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     ALL = [golden_noise_tables, golden_wrap_and_score, golden_neighbors, golden_segment, golden_egnn, golden_atom_types,
-           golden_trajectories, golden_analytical, golden_checkpoint, golden_pair_distances, golden_adaptive_corrector, golden_force_field]
+           golden_trajectories, golden_analytical, golden_checkpoint, golden_pair_distances, golden_adaptive_corrector, golden_force_field, golden_free_lattice]
     wanted = sys.argv[1:]   # e.g. `python oracle/make_golden.py pair_distances`; no argument = everything
     for fn in ALL:
         if not wanted or fn.__name__.replace("golden_", "") in wanted:
