@@ -485,18 +485,23 @@ def pc_sample(
     ending_step_index: int = 0,
     constraint: Optional[Dict[str, torch.Tensor]] = None,
     record: Optional[List] = None,
+    free_lattice: bool = False,
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Fixed-lattice predictor-corrector trajectory.  ``score_fn(A, X, L, sigma) -> (logits, score)``.
+    """Predictor-corrector trajectory.  ``score_fn(A, X, L, sigma) -> (logits, score)``.
 
     ``constraint`` = dict(x0 [Nc,3], a0 [Nc], indices [Nc]) switches on RePaint.  Noise comes from ``tape`` in the
-    reference's per-kind order.  Lattice draws are skipped: with ``use_fixed_lattice_parameters`` they do not
-    influence the result (langevin_generator.py:475-477).
+    reference's per-kind order.  With a fixed lattice the lattice draws are skipped: they do not influence the result
+    (langevin_generator.py:475-477).  ``free_lattice`` (use_fixed_lattice_parameters=False) diffuses the lattice
+    parameters too; the lattice score of the EGNN is identically zero (egnn_score_network.py:296-300), so
+    l <- l + g z in the predictor (:485-490,636-641) and l <- l + sqrt(2 eps) z' in the corrector, where z' is the
+    SECOND lattice draw of the step: the first one only feeds the step size (:758-777).
     """
     T = tables["sigma"].shape[0]
     B, N, d = x.shape
     C = tables["q_matrix"].shape[-1]
     start = T if starting_step_index is None else starting_step_index
     a_cur, x_cur = atom_types.clone(), x.clone()
+    lattice = lattice.clone() if free_lattice else lattice
 
     def repaint(a_in, x_in, index_i):  # constrained_langevin_generator.py:136-163
         idx = constraint["indices"]
@@ -533,6 +538,8 @@ def pc_sample(
             assert (a_new != C - 1).all(), "There remains MASKED atoms at the last time step"
         z = tape.normal("coordinates", B, N, d)
         x_cur = coordinates_update(x_cur, score, sigma_i, tables["g_squared"][idx], tables["g"][idx], z)
+        if free_lattice:
+            lattice = lattice + tables["g"][idx] * tape.normal("lattice", B, lattice.shape[1])
         a_cur = a_new
         if constraint is not None:
             a_cur, x_cur = repaint(a_cur, x_cur, i)
@@ -548,6 +555,9 @@ def pc_sample(
             z = tape.normal("coordinates", B, N, d)
             eps_i = tables["epsilon"][i]
             x_cur = coordinates_update(x_cur, score, sigma_c, eps_i, torch.sqrt(2 * eps_i), z)
+            if free_lattice:
+                tape.normal("lattice", B, lattice.shape[1])  # z_lattice: consumed by the step-size hook only
+                lattice = lattice + torch.sqrt(2 * eps_i) * tape.normal("lattice", B, lattice.shape[1])
             if atom_type_transition_in_corrector:
                 gumbel = tape.gumbel(small_epsilon, B, N, C)
                 binary = tape.uniform("binary", B, N) if greedy else None

@@ -158,3 +158,23 @@ def test_analytical_trajectory():
     # the samples sit within a few sigma_d of the equilibrium positions
     d0 = (x - g["x0"]).abs()
     assert torch.minimum(d0, 1.0 - d0).max() < 0.08
+
+
+def test_free_lattice_trajectory():
+    """use_fixed_lattice_parameters=False: the oracle's lattice diffusion against the reference's trajectory."""
+    g = load_golden("free_lattice")
+    sd = sub_dict(g, "sd")
+    hp = hyper_parameters("radial_sige")
+    T, n_corr = int(g["T"]), int(g["n_corr"])
+    tables = oracle.noise_tables(T, 3, sigma_min=0.005, sigma_max=0.5)
+    B = g["x0"].shape[0]
+
+    def score_fn(at, x, lat, sigma):
+        return oracle.egnn_score_forward(sd, hp, at, x, lat, torch.full((B, 1), sigma))
+
+    a, x, lattice = oracle.pc_sample(score_fn, tables, g["a0"], g["x0"], g["l"], oracle.NoiseTape(80),
+                                     number_of_corrector_steps=n_corr, free_lattice=True)
+    assert torch.equal(a, g["final_a"])
+    torch.testing.assert_close(lattice, g["final_l"], rtol=1e-6, atol=1e-6)
+    d = (x - g["final_x"]).abs()
+    assert torch.minimum(d, 1 - d).max() < 2e-5
