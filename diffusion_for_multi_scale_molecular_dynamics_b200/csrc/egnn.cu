@@ -83,6 +83,7 @@ int64_t carve_workspace(const b200md_egnn_config& cfg, int64_t B, int32_t N, int
   ws.z = (float*)at(take(BN * D * 4)); ws.xcur = (float*)at(take(BN * D * 4)); ws.xagg = (float*)at(take(BN * D * 4));
   ws.h = (float*)at(take(BN * H * 4)); ws.P = (float*)at(take(BN * M * 4)); ws.Q = (float*)at(take(BN * M * 4));
   ws.agg = (float*)at(take(BN * M * 4));
+  ws.U = (float*)at(take(BN * H * 4));
   ws.deg = (int32_t*)at(take(BN * 4)); ws.row_ptr = (int32_t*)at(take((BN + 1) * 4));
   ws.bitmask = (uint32_t*)at(take(BN * W * 4));
   ws.struct_total = (int32_t*)at(take(B * 4)); ws.struct_off = (int32_t*)at(take((B + 1) * 4));
@@ -560,6 +561,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
   } else if (impl != B200MD_IMPL_FFMA) {
     return B200MD_ERR_INVALID_ARGUMENT;
   }
+  if (use_tc && edge_precision == 2 && tc_node_supported(cfg, 2)) precision = 2;   // node kernel in tensor memory too
   const bool use_tc_node = use_tc && tc_node_supported(cfg, precision);
   const int64_t BN = B * N;
   const bool radial = cfg.flags & B200MD_EGNN_RADIAL_CUTOFF;

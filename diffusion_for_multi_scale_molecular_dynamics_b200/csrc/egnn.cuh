@@ -37,6 +37,7 @@ int build_layout(const b200md_egnn_config& cfg, EgnnLayout& lay);
 
 struct EgnnWorkspace {
   float *z, *xcur, *xagg, *h, *P, *Q, *agg;
+  float* U;   // h W0a^T + b0 of the next node update (egnn_node_ts.cuh): [B N, H]
   int32_t *deg, *row_ptr, *struct_total, *struct_off, *n_edges, *edge_src, *edge_dst;
   uint32_t* bitmask;
   int64_t bytes;

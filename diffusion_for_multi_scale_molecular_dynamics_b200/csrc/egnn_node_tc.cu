@@ -272,13 +272,15 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
   pipe.teardown();
 }
 
+#include "egnn_node_ts.cuh"
+
 }  // namespace
 
 bool tc_node_supported(const b200md_egnn_config& cfg, int precision) {
   const int H = cfg.node_hidden, M = cfg.message_hidden;
-  const int chunk = precision == kF16x3 ? 64 : 32;
+  const int chunk = precision == kTf32x3 ? 32 : 64;
   if (H % chunk || M % chunk || H > kMaxN || M > kMaxN || H < chunk || M < chunk) return false;
-  if (cfg.node_n_hidden + 2 + 2 > kMaxGemms) return false;
+  if (cfg.node_n_hidden + 2 + 3 > kMaxGemms) return false;
   return true;
 }
 
@@ -359,6 +361,55 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
   a.bloch = lay.bloch; a.proj = lay.proj; a.embed_w = lay.embed_w; a.embed_b = lay.embed_b;
   a.readout_w = lay.readout_w; a.readout_b = lay.readout_b;
 
+  if (precision == kF16x3Ts) {
+    // the same call in tensor-memory form: the first node Linear split into agg W0b^T (here) + U = h W0a^T + b0 (made
+    // by the previous call, next to P and Q)
+    NodeTsArgs t{};
+    t.wtc = p.wtc; t.packed = packed;
+    int n = 0;
+    auto f16 = [&](int64_t image, int K, int N) { return image + f16_image_offset(K, N); };
+    if (call.update_layer >= 0) {
+      const EgnnLayerOffsets& Lo = lay.layer[call.update_layer];
+      const int64_t base = (int64_t)call.update_layer * lay.tc_node_stride;
+      const int64_t w0 = f16(base + im.w0, H + M, H);
+      t.g[n] = NodeTsGemm{M, H, kNodeChainAddU, 1, 0, 0, w0 + (int64_t)(H / 64) * 2 * H * 32, -1, nullptr}; ++n;
+      for (int i = 0; i < cfg.node_n_hidden; ++i) {
+        t.g[n] = NodeTsGemm{H, H, kNodeChain, 1, 0, 0, f16(base + im.hidden + i * weight_image_floats(H, H), H, H),
+                            Lo.node_hidden_b + (int64_t)i * H, nullptr}; ++n;
+      }
+      t.g[n] = NodeTsGemm{H, H, kNodeChainLast, 1, 0, 0, f16(base + im.last, H, H), Lo.node_last_b, nullptr}; ++n;
+    }
+    if (call.pq_layer >= 0) {
+      const EgnnLayerOffsets& Lo = lay.layer[call.pq_layer];
+      const int64_t base = (int64_t)call.pq_layer * lay.tc_node_stride;
+      t.g[n] = NodeTsGemm{H, M, kNodeOut, 1, 0, 1, f16(base + im.wa, H, M), Lo.msg_b0, call.ws->P}; ++n;
+      t.g[n] = NodeTsGemm{H, M, kNodeOut, 0, 1, 1, f16(base + im.wb, H, M), -1, call.ws->Q}; ++n;
+      t.g[n] = NodeTsGemm{H, H, kNodeOut, 0, 1, 0, f16(base + im.w0, H + M, H), Lo.node_b0, call.ws->U}; ++n;
+    }
+    t.n_gemms = n;
+    t.do_embed = call.embed; t.do_update = call.update_layer >= 0; t.do_readout = call.readout;
+    t.atom_types = call.atom_types; t.x_rel = call.x_rel; t.sigma = call.sigma; t.sigma_scalar = call.sigma_scalar;
+    t.z = call.ws->z; t.xcur = call.ws->xcur; t.xagg = call.ws->xagg; t.h = call.ws->h; t.agg = call.ws->agg;
+    t.U = call.ws->U; t.deg = call.ws->deg;
+    t.logits_out = call.logits_out; t.score_out = call.score_out; t.status = call.status;
+    t.n_nodes = call.n_nodes; t.n_atoms = call.n_atoms;
+    t.C = lay.C; t.F0 = lay.F0; t.D = lay.D; t.H = H; t.M = M; t.nb = lay.nb;
+    t.residual = a.residual; t.coords_mean = a.coords_mean; t.message_mean = a.message_mean; t.mask_logit = call.mask_logit;
+    t.bloch = lay.bloch; t.proj = lay.proj; t.embed_w = lay.embed_w; t.embed_b = lay.embed_b;
+    t.readout_w = lay.readout_w; t.readout_b = lay.readout_b;
+    const size_t ts_bytes = node_ts_smem(n).total + 1024;
+    static bool ts_attr_set = false;
+    if (!ts_attr_set) {
+      cudaError_t e0 = cudaFuncSetAttribute(egnn_node_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e0 != cudaSuccess) return set_cuda_error(e0);
+      ts_attr_set = true;
+    }
+    const int64_t tiles = ceil_div64(call.n_nodes, kTileM);
+    const unsigned grid = (unsigned)(tiles < 1 ? 1 : (tiles > tc_sm_count() ? tc_sm_count() : tiles));
+    { ProfileScope ps__(B200MD_KERNEL_NODE, st); egnn_node_ts_kernel<<<grid, kTsThreads, ts_bytes, st>>>(t); }
+    B200MD_CHECK_LAUNCH();
+    return B200MD_OK;
+  }
   const size_t smem = node_smem(p.n_gemms).total + 1024;
   static bool attr_set = false;
   if (!attr_set) {

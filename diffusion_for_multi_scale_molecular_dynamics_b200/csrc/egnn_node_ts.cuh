@@ -1,0 +1,428 @@
+// EGNN node kernel with the activations in TENSOR MEMORY (the node-side sibling of egnn_edge_ts.cuh).  Included by
+// egnn_node_tc.cu inside its anonymous namespace.
+//
+// Reference arithmetic: models/egnn.py:162-187 (node_model), :212-215 (coord += agg), :376-379 (embedding, read-out),
+// models/score_networks/egnn_score_network.py:165-224,276-281, models/score_networks/score_network.py:183-185.
+//
+// The node MLP's first Linear acts on [h | agg] (K = H + M = 512): too wide to sit beside a 256-column accumulator.
+// It is split like the first message Linear already is: U = h W0a^T + b0 is produced by the call that produces h (next
+// to P and Q, same A operand), and the update call computes agg W0b^T and adds U in the epilogue.  Every GEMM is then
+// K, N <= 256 and the program of a tile is
+//     chain : A0 = agg / deg -> [+U, SiLU] -> n x [Linear, SiLU] -> [Linear + bias + residual = h', stored]     (update)
+//     out   : P = h' Wa^T + b, Q = h' Wb^T, U = h' W0a^T + b0  (three GEMMs sharing the A operand h')        (a layer follows)
+// Chain GEMMs alternate the two 256-column TMEM buffers (accumulator converted IN PLACE into the next A operand, as in
+// the edge kernel); the three output GEMMs keep h' in one buffer and reuse the other as accumulator, so each waits for
+// the epilogue to have drained the previous one ("d_free").
+//
+// Warps (10): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue (two per TMEM lane quarter,
+// 32 columns per thread and chunk).
+#pragma once
+
+#include "ts_common.cuh"
+
+enum NodeGemmKind {
+  kNodeChain = 0,       // v = silu(acc + bias)                      -> next A
+  kNodeChainAddU = 1,   // v = silu(acc + U[node])                   -> next A
+  kNodeChainLast = 2,   // v = acc + bias (+ h) ; h <- v             -> next A when an output group follows
+  kNodeOut = 3,         // out[node] = acc + bias                     (P, Q, U)
+};
+
+struct NodeTsGemm {
+  int K, N, kind;
+  int fresh_a;          // the MMA waits for the epilogue to publish the A chunks (else: same A as the previous GEMM)
+  int wait_d_free;      // the accumulator buffer still holds the previous output: wait until the epilogue drained it
+  int signal_d_free;    // ... and the epilogue says so after draining this one
+  int64_t w16;          // offset (floats) in wtc of the fp16 image of the first K chunk
+  int64_t bias;         // offset in packed, or -1
+  float* out;           // kNodeOut: destination [n_nodes, N]
+};
+
+struct NodeTsArgs {
+  const float* wtc;
+  const float* packed;
+  int n_gemms;
+  NodeTsGemm g[kMaxGemms];
+  int do_embed, do_update, do_readout;
+  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar;
+  float *z, *xcur, *xagg, *h, *agg;
+  const float* U;
+  const int32_t* deg;
+  float* logits_out; float* score_out; int32_t* status;
+  int64_t n_nodes; int32_t n_atoms;
+  int C, F0, D, H, M, nb;
+  int residual, coords_mean, message_mean, mask_logit;
+  int64_t bloch, proj, embed_w, embed_b, readout_w, readout_b;
+};
+
+struct NodeTsSmem {
+  uint32_t b, bars, tmem_slot, bias, total;
+};
+__host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
+  NodeTsSmem L;
+  uint32_t o = 0;
+  L.b = o; o += kTsBStages * kTsBStageBytes;
+  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit + 1) * 8;
+  L.tmem_slot = o; o += 16;
+  o = (o + 15u) & ~15u;   // the bias rows are read with 128-bit shared loads
+  L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
+  L.total = o;
+  return L;
+}
+
+struct NodeTsBars {
+  uint32_t bar0;
+  __device__ __forceinline__ uint32_t b_full(uint32_t s) const { return bar0 + 8u * s; }
+  __device__ __forceinline__ uint32_t b_empty(uint32_t s) const { return bar0 + 8u * (kTsBStages + s); }
+  __device__ __forceinline__ uint32_t a_full(uint32_t slot, uint32_t part) const {
+    return bar0 + 8u * (2 * kTsBStages + slot * kTsParts + part);
+  }
+  __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
+    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
+  }
+  __device__ __forceinline__ uint32_t d_free() const { return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit); }
+};
+
+__device__ __forceinline__ void load_cols(const float* p, float (&v)[kTsCols]) {
+#pragma unroll
+  for (int j = 0; j < kTsCols / 4; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void store_cols(float* p, const float (&v)[kTsCols]) {
+#pragma unroll
+  for (int j = 0; j < kTsCols / 4; ++j)
+    *reinterpret_cast<float4*>(p + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+__global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeTsArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const NodeTsSmem L = node_ts_smem(a.n_gemms);
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias);
+  const float* Wp = a.packed;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (int)((a.n_nodes + kTileM - 1) / kTileM);
+  const int H = a.H, M = a.M, D = a.D;
+
+  for (int t = threadIdx.x; t < a.n_gemms * kMaxN; t += kTsThreads) {
+    const int g = t / kMaxN, n = t - g * kMaxN;
+    s_bias[t] = (n < a.g[g].N && a.g[g].bias >= 0) ? Wp[a.g[g].bias + n] : 0.f;
+  }
+  const uint32_t s_base = smem_u32(smem);
+  NodeTsBars bars;
+  bars.bar0 = s_base + L.bars;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTsBStages; ++s) { mbar_init(bars.b_full(s), 1); mbar_init(bars.b_empty(s), 1); }
+    for (int s = 0; s < kTsSlots; ++s)
+      for (int j = 0; j < kTsParts; ++j) mbar_init(bars.a_full(s, j), 4);
+    for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(bars.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
+    mbar_init(bars.d_free(), kTsEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(s_base + L.tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base_all = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
+  const int n_iterations = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ===== weight producer =====
+    if (lane == 0) {
+      uint32_t cb = 0;
+      for (int it = 0; it < n_iterations; ++it)
+        for (int g = 0; g < a.n_gemms; ++g) {
+          const NodeTsGemm& G = a.g[g];
+          const int nk = G.K / 64, nh = G.N / kTsNSplit;
+          const uint32_t bytes = (uint32_t)nh * kRowBytes;
+          const int64_t part_floats = (int64_t)G.N * (kRowBytes / 4);
+          const float* src = a.wtc + G.w16;
+          for (int h = 0; h < kTsNSplit; ++h)
+            for (int part = 0; part < 2 * nk; ++part, ++cb) {
+              const uint32_t s = cb % kTsBStages;
+              mbar_wait(bars.b_empty(s), ((cb / kTsBStages) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(bars.b_full(s), bytes);
+              bulk_g2s(s_base + L.b + s * kTsBStageBytes, src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4),
+                       bytes, bars.b_full(s));
+            }
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (whole warp converged, elected lane issues; see egnn_edge_ts.cuh) =====
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_all, 0);
+    const uint32_t b_ring = s_base + L.b;
+    const bool leader = elect_one();
+    uint32_t cb = 0, mca = 0, abuf = 0, df = 0;
+    uint32_t use0 = 0, use1 = 0;   // completed uses of each accumulator buffer (phase of its acc_full barriers): unused here
+    (void)use0; (void)use1;
+    for (int it = 0; it < n_iterations; ++it)
+      for (int g = 0; g < a.n_gemms; ++g) {
+        const NodeTsGemm& G = a.g[g];
+        const int nk = G.K / 64, nh = G.N / kTsNSplit;
+        const uint32_t idesc = make_idesc(nh, 0u);
+        const uint32_t a_col = abuf * kMaxN, d_col = a_col ^ kMaxN;
+        if (G.wait_d_free) { mbar_wait(bars.d_free(), df & 1u); ++df; tc_fence_after(); }
+        for (int h = 0; h < kTsNSplit; ++h) {
+          const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
+          for (int c = 0; c < nk; ++c) {
+            const uint32_t s1 = cb % kTsBStages, s2 = (cb + 1) % kTsBStages;
+            mbar_wait(bars.b_full(s1), (cb / kTsBStages) & 1u);
+            mbar_wait(bars.b_full(s2), ((cb + 1) / kTsBStages) & 1u);
+            const uint32_t bd1 = desc_lo_sw128(b_ring + s1 * kTsBStageBytes), bd2 = desc_lo_sw128(b_ring + s2 * kTsBStageBytes);
+            const uint32_t chunk = mca + (uint32_t)c;
+            const uint32_t a_chunk = tmem_base + a_col + (uint32_t)(c * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (G.fresh_a && h == 0 && (j % (4 / kTsParts)) == 0)
+                mbar_wait(bars.a_full(chunk % kTsSlots, j / (4 / kTsParts)), (chunk / kTsSlots) & 1u);
+              tc_fence_after();
+              if (leader) {
+                umma_f16_ts(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);
+                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescNegateA, 1u);
+                umma_f16_ts(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);
+              }
+            }
+            if (leader) {
+              umma_commit(bars.b_empty(s1));
+              umma_commit(bars.b_empty(s2));
+            }
+            __syncwarp();
+            cb += 2;
+          }
+          if (leader) umma_commit(bars.acc_full(d_col / kMaxN, h));
+          __syncwarp();
+        }
+        if (G.fresh_a) mca += nk;
+        const bool becomes_a = (G.kind == kNodeChain || G.kind == kNodeChainAddU ||
+                                (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
+        if (becomes_a) abuf ^= 1u;
+      }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_taddr = tmem_base_all + ((uint32_t)(q * 32) << 16);
+    const uint32_t sa_bias = s_base + L.bias;
+    uint32_t ca = 0, abuf = 0;
+    uint32_t uses[2] = {0u, 0u};
+    unsigned local_status = 0;
+    float checksum = 0.f;   // inf / NaN of an fp16 overflow propagates into everything stored: one test at the end
+
+    auto publish = [&](uint32_t col, const float (&v)[kTsCols]) {
+      uint32_t w[kTsCols];
+      split_hi_lo(v, w);
+#pragma unroll
+      for (int i = 0; i < kTsCols / 16; ++i) tmem_st16(lane_taddr + col + 16 * i, w + 16 * i);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.a_full(ca % kTsSlots, part));
+      ++ca;
+    };
+
+    for (int it = 0; it < n_iterations; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int64_t node = (int64_t)tile * kTileM + row;
+      const bool valid = node < a.n_nodes;
+      const float degf = valid ? fmaxf((float)a.deg[node], 1.0f) : 1.0f;
+      float sg = 0.f;
+      int atc = 0;
+      if (a.do_embed && valid) {
+        const int64_t at = a.atom_types[node];
+        sg = a.sigma ? a.sigma[node / a.n_atoms] : a.sigma_scalar;
+        if (part == 0) {
+          if (at < 0 || at >= a.C) local_status |= B200MD_STATUS_A_OUT_OF_RANGE;
+          if (!(sg > 0.f)) local_status |= B200MD_STATUS_SIGMA_OUT_OF_RANGE;
+        }
+        atc = (int)min(max(at, (int64_t)0), (int64_t)(a.C - 1));
+      }
+      if (part == 0 && valid) {
+        if (a.do_embed) {
+          // uplift z = [cos(2 pi k.x), sin(2 pi k.x)] per Bloch vector   egnn_score_network.py:196-224
+          const float two_pi = 6.283185307179586f;
+          float xr[3];
+          for (int s = 0; s < 3; ++s) {
+            xr[s] = a.x_rel[node * 3 + s];
+            if (!(xr[s] >= 0.0f && xr[s] < 1.0f)) local_status |= B200MD_STATUS_X_OUT_OF_RANGE;
+          }
+          for (int b = 0; b < a.nb; ++b) {
+            float kr = 0.f;
+            for (int s = 0; s < 3; ++s) kr += Wp[a.bloch + b * 3 + s] * (two_pi * xr[s]);
+            float sn, cs;
+            sincosf(kr, &sn, &cs);
+            a.z[node * D + 2 * b] = cs; a.z[node * D + 2 * b + 1] = sn;
+            a.xcur[node * D + 2 * b] = cs; a.xcur[node * D + 2 * b + 1] = sn;
+            a.xagg[node * D + 2 * b] = 0.f; a.xagg[node * D + 2 * b + 1] = 0.f;
+          }
+        }
+        if (a.do_update) {  // coord += agg   models/egnn.py:212-215
+          for (int d = 0; d < D; ++d) {
+            float v = a.xagg[node * D + d];
+            if (a.coords_mean) v = v / degf;
+            a.xcur[node * D + d] += v;
+            a.xagg[node * D + d] = 0.f;
+          }
+        }
+      }
+
+      // ---- first A operand of the tile ----
+      const uint32_t a_col0 = abuf * kMaxN;
+      if (a.do_embed) {
+        // h = W_in [sigma, onehot(a)] + b   egnn_score_network.py:165-194, egnn.py:376
+        for (int c = 0; c < H / 64; ++c) {
+          const int col0 = c * 64 + part * kTsCols;
+          float v[kTsCols];
+#pragma unroll
+          for (int j = 0; j < kTsCols; ++j) {
+            const int o = col0 + j;
+            v[j] = valid ? Wp[a.embed_b + o] + (Wp[a.embed_w + o * a.F0] * sg + Wp[a.embed_w + o * a.F0 + 1 + atc]) : 0.f;
+          }
+          if (valid) store_cols(a.h + node * H + col0, v);
+          publish(a_col0 + (uint32_t)col0, v);
+        }
+        if (valid) {
+          float zero[kTsCols];
+#pragma unroll
+          for (int j = 0; j < kTsCols; ++j) zero[j] = 0.f;
+          for (int c = 0; c < M / 64; ++c) store_cols(a.agg + node * M + c * 64 + part * kTsCols, zero);
+        }
+      } else {
+        // aggregated messages (mean: / max(deg, 1)), reset for the next layer   models/egnn.py:178-183
+        for (int c = 0; c < M / 64; ++c) {
+          const int col0 = c * 64 + part * kTsCols;
+          float v[kTsCols];
+          if (valid) {
+            float* ap = a.agg + node * M + col0;
+            load_cols(ap, v);
+            if (a.message_mean) {
+#pragma unroll
+              for (int j = 0; j < kTsCols; ++j) v[j] = v[j] / degf;
+            }
+            float zero[kTsCols];
+#pragma unroll
+            for (int j = 0; j < kTsCols; ++j) zero[j] = 0.f;
+            store_cols(ap, zero);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
+          }
+          publish(a_col0 + (uint32_t)col0, v);
+        }
+      }
+
+      // ---- the GEMMs ----
+      for (int g = 0; g < a.n_gemms; ++g) {
+        const NodeTsGemm& G = a.g[g];
+        const uint32_t dbuf = abuf ^ 1u;
+        const uint32_t d_col = dbuf * kMaxN;
+        const int nchunks = G.N / 64, nh = G.N / kTsNSplit;
+        const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
+        const bool becomes_a = (G.kind == kNodeChain || G.kind == kNodeChainAddU ||
+                                (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
+        int waited = -1;
+        for (int c = 0; c < nchunks; ++c) {
+          const int need = (c * 64 + 64 + nh - 1) / nh - 1;
+          if (need > waited) {
+            mbar_wait(bars.acc_full(dbuf, need), uses[dbuf] & 1u);
+            tc_fence_after();
+            waited = need;
+          }
+          const int col0 = c * 64 + part * kTsCols;
+          uint32_t r[kTsCols];
+          float v[kTsCols];
+          tmem_load_cols(lane_taddr + d_col + col0, r);
+          if (G.kind == kNodeChain) {
+#pragma unroll
+            for (int j = 0; j < kTsCols / 4; ++j) {
+              const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
+              silu2(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
+              silu2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else if (G.kind == kNodeChainAddU) {
+            float u[kTsCols];
+            if (valid) {
+              load_cols(a.U + node * H + col0, u);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kTsCols; ++j) u[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < kTsCols / 2; ++j)
+              silu2(add2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), pack2(u[2 * j], u[2 * j + 1])), v[2 * j], v[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kTsCols / 4; ++j) {
+              const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+            }
+            if (G.kind == kNodeChainLast) {
+              if (valid) {
+                if (a.residual) {
+                  float old[kTsCols];
+                  load_cols(a.h + node * H + col0, old);
+#pragma unroll
+                  for (int j = 0; j < kTsCols; ++j) v[j] = old[j] + v[j];
+                }
+                store_cols(a.h + node * H + col0, v);
+              }
+            } else if (valid) {
+              store_cols(G.out + node * G.N + col0, v);
+            }
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < kTsCols; ++j) checksum += v[j];
+            }
+          }
+          if (becomes_a) publish(d_col + (uint32_t)col0, v);
+        }
+        ++uses[dbuf];
+        if (G.signal_d_free) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars.d_free());
+        }
+        if (becomes_a) abuf ^= 1u;
+      }
+
+      if (a.do_readout) {
+        __threadfence_block();
+        ts_epilogue_barrier();  // every column of every h row of the tile is in memory
+        if (part == 0 && valid) {
+          // logits = W_c h + b_c (egnn.py:379); MASK logit -> -inf (score_network.py:183-185)
+          for (int c = 0; c < a.C; ++c) {
+            float s = 0.f;
+            for (int k = 0; k < H; ++k) s = fmaf(Wp[a.readout_w + c * H + k], a.h[node * H + k], s);
+            float v = s + Wp[a.readout_b + c];
+            if (a.mask_logit && c == a.C - 1) v = -CUDART_INF_F;
+            a.logits_out[node * a.C + c] = v;
+          }
+          // S^alpha = z . Gamma^alpha . zhat   egnn_score_network.py:276-281
+          for (int al = 0; al < 3; ++al) {
+            float s = 0.f;
+            for (int i = 0; i < D; ++i) {
+              float inner = 0.f;
+              for (int j = 0; j < D; ++j) inner += Wp[a.proj + (al * D + i) * D + j] * a.xcur[node * D + j];
+              s += a.z[node * D + i] * inner;
+            }
+            a.score_out[node * 3 + al] = s;
+          }
+        }
+        ts_epilogue_barrier();
+      }
+    }
+    if (!(fabsf(checksum) <= CUDART_MAX_NORMAL_F)) local_status |= B200MD_STATUS_TC_RANGE;
+    if (local_status && a.status) atomicOr(a.status, (int)local_status);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base_all, kTmemCols);
+  }
+}

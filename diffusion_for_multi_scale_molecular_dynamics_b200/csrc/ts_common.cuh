@@ -1,0 +1,145 @@
+// Shared pieces of the "activations in tensor memory" kernels (egnn_edge_ts.cuh, egnn_node_ts.cuh): geometry of the
+// epilogue (two fat warps per TMEM lane quarter, 32 accumulator columns per thread and chunk), the tcgen05.mma .ts /
+// tcgen05.ld / tcgen05.st wrappers, the hi / -lo split, packed fp32 arithmetic and the SiLU.
+// Include inside namespace b200md (after tc_common.cuh, with `using namespace tc`).
+#pragma once
+
+#ifndef B200MD_TS_NSPLIT
+#define B200MD_TS_NSPLIT 2
+#endif
+constexpr int kTsNSplit = B200MD_TS_NSPLIT;       // column groups of an accumulator, computed one after the other
+constexpr int kTsBStageBytes = (kMaxN / kTsNSplit) * kRowBytes;   // one weight part of a K chunk for ONE column group
+constexpr int kTsBStages = 3 * kTsNSplit * 2;     // 192 KB in all
+constexpr int kTsSlots = 4;                       // K-chunk slots of the "A ready" barriers
+constexpr int kTsParts = 2;                       // epilogue warps per lane quarter
+constexpr int kTsCols = 64 / kTsParts;            // accumulator columns one epilogue thread converts per chunk
+constexpr int kTsEpiWarps = 4 * kTsParts;
+constexpr int kTsThreads = 32 * (2 + kTsEpiWarps);
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T
+// `b_desc_lo`: low word of the K-major SWIZZLE_128B descriptor (desc_lo_sw128); the high word is a constant.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 bd;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 bd, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_desc_lo), "r"(idesc), "r"(accumulate), "n"(kDescHiSw128)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// tcgen05.ld in two halves, so independent work can be placed between the issue and the wait; the wait names the
+// registers as in/out operands, which keeps every use of them after it
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// kTsCols accumulator columns of this lane -> registers (complete on return)
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[kTsCols]) {
+#pragma unroll
+  for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(taddr + 16 * i, r + 16 * i);
+#pragma unroll
+  for (int i = 0; i < kTsCols / 16; ++i) tmem_ld_wait16(r + 16 * i);
+}
+// two fp32 -> packed f16x2 (first argument in the LOW half); out-of-range values become +-inf (no saturation): they
+// poison the chain and are caught by the finite check on the tile's result
+__device__ __forceinline__ uint32_t pack_f16x2_inf(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// kTsCols activations -> per K step (16 values) [hi x 8 | -lo x 8] packed fp16 pairs: the A-operand image of those
+// columns.  hi = fp16(x); the second part holds fp16(hi - x) = -lo, one mixed-precision subtract per element
+// (sub.f32.f16, SASS FHADD) instead of an unpack and a subtract; the A_2 B_1 MMA negates it back (a_negate bit of the
+// instruction descriptor).
+__device__ __forceinline__ void split_hi_lo(const float (&v)[kTsCols], uint32_t (&w)[kTsCols]) {
+#pragma unroll
+  for (int s = 0; s < kTsCols / 16; ++s)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x0 = v[16 * s + 2 * i], x1 = v[16 * s + 2 * i + 1];
+      const uint32_t hi = pack_f16x2_inf(x0, x1);
+      float n0, n1;
+      asm("{\n"
+          ".reg .b16 h0, h1;\n"
+          "mov.b32 {h0, h1}, %2;\n"
+          "sub.rn.f32.f16 %0, h0, %3;\n"
+          "sub.rn.f32.f16 %1, h1, %4;\n"
+          "}\n"
+          : "=f"(n0), "=f"(n1)
+          : "r"(hi), "f"(x0), "f"(x1));
+      w[16 * s + i] = hi;
+      w[16 * s + 8 + i] = pack_f16x2_inf(n0, n1);
+    }
+}
+constexpr uint32_t kIdescNegateA = 1u << 13;
+
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes per instruction) for the bias add and the SiLU arithmetic.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// (silu(x0), silu(x1)) of a packed pair: x / (1 + 2^(-x log2 e)) with the SFU exp2 / reciprocal (about 2 ulp each, far
+// below the 1e-5 parity bound).  Moving the reciprocal to three Newton steps on the FMA pipe halves the SFU load but
+// does not change the launch time: at this point the kernel is limited by the 1000 W power cap, not by a pipe.
+__device__ __forceinline__ void silu2(uint64_t x, float& o0, float& o1) {
+  float t0, t1, e0, e1, r0, r1;
+  unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), t0, t1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+  unpack2(mul2(x, pack2(r0, r1)), o0, o1);
+}
+// shared-memory load by window address (keeps the access an LDS: pointers derived from the aligned dynamic-smem base
+// lose their address space and become generic loads)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void ts_epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(kTsEpiWarps * 32) : "memory"); }
