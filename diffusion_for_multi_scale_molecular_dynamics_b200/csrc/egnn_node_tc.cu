@@ -281,6 +281,7 @@ bool tc_node_supported(const b200md_egnn_config& cfg, int precision) {
   const int chunk = precision == kTf32x3 ? 32 : 64;
   if (H % chunk || M % chunk || H > kMaxN || M > kMaxN || H < chunk || M < chunk) return false;
   if (cfg.node_n_hidden + 2 + 3 > kMaxGemms) return false;
+  if (precision == kF16x3Ts && cfg.num_atom_types + 1 > kNodeMaxClasses) return false;   // logits kept in registers
   return true;
 }
 

@@ -54,8 +54,10 @@ struct NodeTsArgs {
   int64_t bloch, proj, embed_w, embed_b, readout_w, readout_b;
 };
 
+constexpr int kNodeMaxClasses = 8;
+
 struct NodeTsSmem {
-  uint32_t b, bars, tmem_slot, bias, total;
+  uint32_t b, bars, tmem_slot, bias, readout, logits, total;
 };
 __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   NodeTsSmem L;
@@ -65,6 +67,8 @@ __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   L.tmem_slot = o; o += 16;
   o = (o + 15u) & ~15u;   // the bias rows are read with 128-bit shared loads
   L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
+  L.readout = o; o += kNodeMaxClasses * kMaxN * 4;            // classification weights [C][H]
+  L.logits = o; o += kTsParts * kTileM * kNodeMaxClasses * 4; // partial logits [part][row][C]
   L.total = o;
   return L;
 }
@@ -109,6 +113,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     const int g = t / kMaxN, n = t - g * kMaxN;
     s_bias[t] = (n < a.g[g].N && a.g[g].bias >= 0) ? Wp[a.g[g].bias + n] : 0.f;
   }
+  float* s_readout = reinterpret_cast<float*>(smem + L.readout);
+  float* s_logits = reinterpret_cast<float*>(smem + L.logits);
+  if (a.do_readout)
+    for (int t = threadIdx.x; t < a.C * H; t += kTsThreads) s_readout[(t / H) * kMaxN + (t % H)] = Wp[a.readout_w + t];
   const uint32_t s_base = smem_u32(smem);
   NodeTsBars bars;
   bars.bar0 = s_base + L.bars;
@@ -313,6 +321,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       }
 
       // ---- the GEMMs ----
+      float logit[kNodeMaxClasses];
+#pragma unroll
+      for (int cl = 0; cl < kNodeMaxClasses; ++cl) logit[cl] = 0.f;
       for (int g = 0; g < a.n_gemms; ++g) {
         const NodeTsGemm& G = a.g[g];
         const uint32_t dbuf = abuf ^ 1u;
@@ -370,6 +381,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                 }
                 store_cols(a.h + node * H + col0, v);
               }
+              if (a.do_readout) {   // logits = W_c h + b_c (egnn.py:379): partial dot products while h' is in registers
+#pragma unroll
+                for (int cl = 0; cl < kNodeMaxClasses; ++cl)
+                  if (cl < a.C) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kTsCols / 4; ++j) {
+                      const float4 w = *reinterpret_cast<const float4*>(s_readout + cl * kMaxN + col0 + 4 * j);
+                      acc = fmaf(v[4 * j + 0], w.x, acc); acc = fmaf(v[4 * j + 1], w.y, acc);
+                      acc = fmaf(v[4 * j + 2], w.z, acc); acc = fmaf(v[4 * j + 3], w.w, acc);
+                    }
+                    logit[cl] += acc;
+                  }
+              }
             } else if (valid) {
               store_cols(G.out + node * G.N + col0, v);
             }
@@ -390,14 +415,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       }
 
       if (a.do_readout) {
-        __threadfence_block();
-        ts_epilogue_barrier();  // every column of every h row of the tile is in memory
+#pragma unroll
+        for (int cl = 0; cl < kNodeMaxClasses; ++cl)
+          if (cl < a.C) s_logits[(part * kTileM + row) * kNodeMaxClasses + cl] = logit[cl];
+        ts_epilogue_barrier();
         if (part == 0 && valid) {
-          // logits = W_c h + b_c (egnn.py:379); MASK logit -> -inf (score_network.py:183-185)
+          // MASK logit -> -inf (score_network.py:183-185)
           for (int c = 0; c < a.C; ++c) {
-            float s = 0.f;
-            for (int k = 0; k < H; ++k) s = fmaf(Wp[a.readout_w + c * H + k], a.h[node * H + k], s);
-            float v = s + Wp[a.readout_b + c];
+            float v = Wp[a.readout_b + c];
+#pragma unroll
+            for (int pp = 0; pp < kTsParts; ++pp) v += s_logits[(pp * kTileM + row) * kNodeMaxClasses + c];
             if (a.mask_logit && c == a.C - 1) v = -CUDART_INF_F;
             a.logits_out[node * a.C + c] = v;
           }

@@ -142,4 +142,5 @@ __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ts_epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(kTsEpiWarps * 32) : "memory"); }
