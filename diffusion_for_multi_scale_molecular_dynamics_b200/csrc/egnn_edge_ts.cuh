@@ -260,12 +260,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     };
     // chunk c of the first activation of a tile: silu(P[src] + Q[dst] + radial * w_r) -> A operand at a_col
     auto prefetch_first = [&](const Edge& ed, int c) {
+#ifndef B200MD_TS_NO_PREFETCH
       if (ed.valid) {
         const float* pp = a.P + (int64_t)ed.src * M + c * 64 + part * kTsCols;
         const float* qq = a.Q + (int64_t)ed.dst * M + c * 64 + part * kTsCols;
         prefetch_l1(pp);
         prefetch_l1(qq);
       }
+#endif
     };
     auto first_activation_chunk = [&](const Edge& ed, int c, uint32_t a_col) {
       const int col0 = c * 64 + part * kTsCols;
