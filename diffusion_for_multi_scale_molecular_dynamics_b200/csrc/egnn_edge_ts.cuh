@@ -22,6 +22,14 @@
 
 #include "ts_common.cuh"
 
+// CTAs per thread-block cluster.  With 2, the CTAs of a pair walk the same weight stream: each fetches half of every
+// weight stage from L2 and multicasts it into the shared memory of both, which halves the L2 -> SM weight traffic
+// (117 GB per launch at 4096 structures).  Both CTAs run the same number of tiles (the last one may be empty).
+#ifndef B200MD_TS_CLUSTER
+#define B200MD_TS_CLUSTER 2
+#endif
+constexpr int kTsCluster = B200MD_TS_CLUSTER;
+
 struct TsSmem {
   uint32_t b, bars, tmem_slot, bias, wr, wlast, dot, total;
 };
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   pipe.s_base = smem_u32(smem);
   pipe.bar0 = pipe.s_base + L.bars;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), 1); }
+    for (int s = 0; s < kTsBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), kTsCluster); }
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), 4);
     for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(pipe.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
@@ -107,10 +115,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   if (warp == 1) tmem_alloc(pipe.s_base + L.tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (kTsCluster > 1) cluster_sync();   // every CTA's barriers exist before a peer's multicast can reach them
   tc_fence_after();
   pipe.tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
-  const int n_iterations = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // tile schedule: cluster k of n_clusters takes tiles (i n_clusters + k) kTsCluster + rank, i = 0, 1, ...; every CTA of
+  // a cluster runs the same number of iterations (a tile index >= n_tiles is an empty tile)
+  const int n_clusters = (int)gridDim.x / kTsCluster, cluster_id = (int)blockIdx.x / kTsCluster;
+  const int cta_rank = kTsCluster > 1 ? (int)cluster_ctarank() : 0;
+  const int n_groups = (n_tiles + kTsCluster - 1) / kTsCluster;
+  const int n_iterations = n_groups > cluster_id ? (n_groups - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const int first_tile = cluster_id * kTsCluster + cta_rank, tile_stride = n_clusters * kTsCluster;
 #ifdef B200MD_TS_TRACE
   bool trace_on = false;
   unsigned trace_idx = 0;
@@ -133,8 +148,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               const uint32_t s = cb % kTsBStages;
               mbar_wait(pipe.b_empty(s), ((cb / kTsBStages) & 1u) ^ 1u);
               mbar_arrive_expect_tx(pipe.b_full(s), bytes);
-              bulk_g2s(pipe.s_base + L.b + s * kTsBStageBytes, src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4),
-                       bytes, pipe.b_full(s));
+              const float* stage_src = src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4);
+              if (kTsCluster > 1) {   // this CTA's slice of the stage, delivered to every CTA of the cluster
+                const uint32_t slice = bytes / kTsCluster;
+                bulk_g2s_multicast(pipe.s_base + L.b + s * kTsBStageBytes + cta_rank * slice, stage_src + cta_rank * (slice / 4),
+                                   slice, pipe.b_full(s), (uint16_t)((1u << kTsCluster) - 1u));
+              } else {
+                bulk_g2s(pipe.s_base + L.b + s * kTsBStageBytes, stage_src, bytes, pipe.b_full(s));
+              }
             }
         }
     }
@@ -179,9 +200,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);             // A_1 B_2
               }
             }
-            if (leader) {
-              umma_commit(pipe.b_empty(s1));
-              umma_commit(pipe.b_empty(s2));
+            if (leader) {   // a stage is free when EVERY CTA of the cluster has consumed it: the peers write into it too
+              if (kTsCluster > 1) {
+                umma_commit_multicast(pipe.b_empty(s1), (uint16_t)((1u << kTsCluster) - 1u));
+                umma_commit_multicast(pipe.b_empty(s2), (uint16_t)((1u << kTsCluster) - 1u));
+              } else {
+                umma_commit(pipe.b_empty(s1));
+                umma_commit(pipe.b_empty(s2));
+              }
             }
             __syncwarp();
             cb += 2;
@@ -220,7 +246,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     };
     auto load_edge = [&](int it) {
       Edge ed;
-      const int e = ((int)blockIdx.x + it * (int)gridDim.x) * kTileM + row;
+      const int e = (first_tile + it * tile_stride) * kTileM + row;
       ed.valid = e < E;
       ed.src = ed.valid ? a.edge_src[e] : -1;
       ed.dst = ed.valid ? a.edge_dst[e] : -1;
@@ -430,6 +456,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   }
   tc_fence_before();
   __syncthreads();
+  if (kTsCluster > 1) cluster_sync();   // no CTA leaves while a peer may still multicast into it
   tc_fence_after();
   if (warp == 1) {
     __syncwarp();

@@ -348,7 +348,22 @@ int tc_launch_edge_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, i
   }
   if (ts) {
     ProfileScope ps__(B200MD_KERNEL_EDGE, st);
-    egnn_edge_ts_kernel<<<(unsigned)tc_sm_count(), kTsThreads, smem, st>>>(a);
+    if (kTsCluster > 1) {
+      cudaLaunchConfig_t cfg_l{};
+      cfg_l.gridDim = dim3((unsigned)(tc_sm_count() / kTsCluster) * kTsCluster);
+      cfg_l.blockDim = dim3(kTsThreads);
+      cfg_l.dynamicSmemBytes = smem;
+      cfg_l.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kTsCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg_l.attrs = attr;
+      cfg_l.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg_l, egnn_edge_ts_kernel, a);
+      if (e != cudaSuccess) return set_cuda_error(e);
+    } else {
+      egnn_edge_ts_kernel<<<(unsigned)tc_sm_count(), kTsThreads, smem, st>>>(a);
+    }
   } else {
     ProfileScope ps__(B200MD_KERNEL_EDGE, st);
     cudaError_t e = launch_clustered(precision == kF16x3 ? egnn_edge_tc_kernel<kF16x3> : egnn_edge_tc_kernel<kTf32x3>,
