@@ -5,7 +5,6 @@ bandwidth of MEASURED_PEAKS.json.  Bytes are ALGORITHMIC.
 
     python scripts/kernel_rooflines.py > gpurun_out/kernel_rooflines.json
 """
-import ctypes
 import json
 import os
 import sys
@@ -21,8 +20,6 @@ from diffusion_for_multi_scale_molecular_dynamics_b200.namespace import (AXL, AX
                                                                        NOISY_AXL_COMPOSITION)
 from diffusion_for_multi_scale_molecular_dynamics_b200.oracle.energy_oracle_factory import (  # noqa: E402
     create_energy_oracle, create_energy_oracle_parameters)
-from diffusion_for_multi_scale_molecular_dynamics_b200.score.wrapped_gaussian_score import \
-    get_coordinates_sigma_normalized_score  # noqa: E402
 from diffusion_for_multi_scale_molecular_dynamics_b200.utils.basis_transformations import \
     map_relative_coordinates_to_unit_cell  # noqa: E402
 from diffusion_for_multi_scale_molecular_dynamics_b200.utils.structure_utils import compute_distances_in_batch  # noqa: E402
