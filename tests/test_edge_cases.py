@@ -95,3 +95,36 @@ def test_score_network_invariances_at_the_largest_supercell(cuda_device):
     assert (permuted.X - base.X[:, perm.to(cuda_device)]).abs().max() <= 2e-5 * scale + SCORE_CANCELLATION_FLOOR
     assert (permuted.A[finite[:, perm.to(cuda_device)]] - base.A[:, perm.to(cuda_device)][finite[:, perm.to(cuda_device)]]
             ).abs().max() <= 2e-5 * base.A[finite].abs().max()
+
+
+def test_full_size_batch_is_consistent_with_its_parts(cuda_device):
+    """BASELINE config 2 at full size (4096 structures x 64 atoms, production widths, 6.5 M edges: ~340 tiles per CTA,
+    clusters of two CTAs sharing the weight stream): two predictor-corrector steps of the whole batch against the same
+    steps of a 300-structure slice of it taken alone.  The slice lands on different tiles, CTAs and cluster ranks, and the
+    noise is keyed by the global sample index, so the rows must agree (up to the order of the fp32 reductions)."""
+    from diffusion_for_multi_scale_molecular_dynamics_b200.generators.langevin_generator import LangevinGenerator
+    from diffusion_for_multi_scale_molecular_dynamics_b200.generators.predictor_corrector_axl_generator import \
+        PredictorCorrectorSamplingParameters
+    from diffusion_for_multi_scale_molecular_dynamics_b200.namespace import AXL
+    from diffusion_for_multi_scale_molecular_dynamics_b200.noise_schedulers.noise_parameters import NoiseParameters
+    hp = dict(num_atom_types=1, **PRODUCTION)
+    torch.manual_seed(33)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp)).to(cuda_device)
+    B, N, T = 4096, 64, 1000
+    sampling = PredictorCorrectorSamplingParameters(number_of_samples=B, number_of_atoms=N, num_atom_types=1,
+                                                    use_fixed_lattice_parameters=True, cell_dimensions=[10.86] * 3)
+    gen = LangevinGenerator(NoiseParameters(total_time_steps=T), sampling, net)
+    gen.seed = 5
+    x0 = torch.rand(B, N, 3, device=cuda_device)
+    a0 = torch.full((B, N), 1, dtype=torch.long, device=cuda_device)
+    lattice = torch.zeros(B, 6, device=cuda_device)
+    lattice[:, :3] = 10.86
+    full = gen.sample_from_noisy_composition(AXL(A=a0.clone(), X=x0.clone(), L=lattice), T, T - 2)
+    lo, hi = 1717, 2017
+    gen.sample_offset = lo
+    part = gen.sample_from_noisy_composition(AXL(A=a0[lo:hi].clone(), X=x0[lo:hi].clone(), L=lattice[lo:hi]), T, T - 2)
+    gen.sample_offset = 0
+    assert torch.equal(part.A, full.A[lo:hi])
+    d = (part.X - full.X[lo:hi]).abs()
+    assert torch.minimum(d, 1 - d).max() < 2e-5
+    assert bool(((full.X >= 0) & (full.X < 1)).all()) and not torch.equal(full.X, x0)
