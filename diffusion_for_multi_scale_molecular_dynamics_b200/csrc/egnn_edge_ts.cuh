@@ -29,6 +29,17 @@
 #define B200MD_TS_CLUSTER 2
 #endif
 constexpr int kTsCluster = B200MD_TS_CLUSTER;
+// SFU token (ts_common.cuh: sfu_acquire / sfu_release): the two epilogue warps of a scheduler take turns in the SiLU phase
+// (32 ex2 + 32 rcp per thread, SFU-bound) so that one converts / stores while the other occupies the SFU.  Cycle trace:
+// SiLU phase 1050 -> 750 cycles, layer period 8390 -> 8230; 2 % on the power-capped step.  The token is handed on after
+// B200MD_TS_TOKEN_RELEASE + 1 of the kTsCols / 4 column groups (earlier hand-over measured the same).
+#ifndef B200MD_TS_SFU_TOKEN
+#define B200MD_TS_SFU_TOKEN 1
+#endif
+#ifndef B200MD_TS_TOKEN_RELEASE
+#define B200MD_TS_TOKEN_RELEASE 7
+#endif
+constexpr int kTsTokenReleaseAfter = B200MD_TS_TOKEN_RELEASE;
 
 struct TsSmem {
   uint32_t b, bars, tmem_slot, bias, wr, wlast, dot, total;
@@ -227,11 +238,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     const uint32_t sa_bias = pipe.s_base + L.bias, sa_wr = pipe.s_base + L.wr, sa_wlast = pipe.s_base + L.wlast;
     uint32_t ca = 0, gc = 0;
     bool poisoned = false;
+#if B200MD_TS_SFU_TOKEN
+    const uint32_t tok_mine = 2u + 2u * (uint32_t)q + (uint32_t)part, tok_peer = 2u + 2u * (uint32_t)q + (uint32_t)(part ^ 1);
+    if (part == 1) sfu_arrive(tok_peer);   // part 0 goes first
+#endif
     // store the A-operand image of kTsCols columns at `col` of this lane and publish them
     auto publish = [&](uint32_t col, const uint32_t (&w)[kTsCols]) {
 #pragma unroll
       for (int i = 0; i < kTsCols / 16; ++i) tmem_st16(lane_taddr + col + 16 * i, w + 16 * i);
+      TS_TRACE(10, col);
       tmem_wait_st();
+      TS_TRACE(11, col);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pipe.a_full(ca % kTsSlots, part));
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         }
         int waited = -1;
         auto wait_for_chunk = [&](int c) {
-          const int need = (c * 64 + 64 + nh - 1) / nh - 1;   // last column group this chunk reads
+          const int need = ts_last_group_of_chunk(c, nh);
           if (need > waited) {
             TS_TRACE(1, g * 16 + c);
             mbar_wait(pipe.acc_full(gc & 1u, need), (gc >> 1) & 1u);
@@ -363,34 +380,63 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         // v = silu(accumulator + bias)
         auto activate = [&](const uint32_t (&r)[kTsCols], int col0, float (&v)[kTsCols]) {
           TS_TRACE(4, col0);
+#if B200MD_TS_SFU_TOKEN
+          uint32_t dep = 0;
+#pragma unroll
+          for (int j = 0; j < kTsCols / 4; ++j) {
+            const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
+            silu2_dep(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1], dep);
+            silu2_dep(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3], dep);
+            if (j == kTsTokenReleaseAfter) sfu_release(tok_peer, dep);
+          }
+#else
 #pragma unroll
           for (int j = 0; j < kTsCols / 4; ++j) {
             const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
             silu2(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
             silu2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
           }
+#endif
           TS_TRACE(5, col0);
+        };
+        // accumulator columns -> registers; with the SFU token, the turn is taken before the registers become usable
+        auto load_acc = [&](uint32_t taddr, uint32_t (&r)[kTsCols]) {
+#pragma unroll
+          for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(taddr + 16 * i, r + 16 * i);
+#if B200MD_TS_SFU_TOKEN
+          sfu_acquire(tok_mine);
+#endif
+#pragma unroll
+          for (int i = 0; i < kTsCols / 16; ++i) tmem_ld_wait16(r + 16 * i);
         };
         if (!is_last) {
           float v[kTsCols];
           uint32_t r[kTsCols];
           wait_for_chunk(0);
-          tmem_load_cols(lane_taddr + d_col + part * kTsCols, r);
+          load_acc(lane_taddr + d_col + part * kTsCols, r);
           activate(r, part * kTsCols, v);
           for (int c = 0; c < nchunks; ++c) {
             const int col0 = c * 64 + part * kTsCols;
             const bool more = c + 1 < nchunks;
             if (more) {   // the next chunk's accumulator columns travel while this chunk is split and published
               wait_for_chunk(c + 1);
+              TS_TRACE(14, g * 16 + c);
 #pragma unroll
               for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(lane_taddr + d_col + col0 + 64 + 16 * i, r + 16 * i);
+              TS_TRACE(15, g * 16 + c);
             }
             uint32_t w[kTsCols];
             split_hi_lo(v, w);
+            TS_TRACE(9, g * 16 + c);
             publish(d_col + (uint32_t)col0, w);
             TS_TRACE(6, g * 16 + c);
             if (is_message) segment_add(cur, v, a.agg + (int64_t)cur.src * M + col0);  // agg[src] += m (models/egnn.py:178-181)
             if (more) {
+              TS_TRACE(12, g * 16 + c);
+#if B200MD_TS_SFU_TOKEN
+              sfu_acquire(tok_mine);
+#endif
+              TS_TRACE(13, g * 16 + c);
 #pragma unroll
               for (int i = 0; i < kTsCols / 16; ++i) tmem_ld_wait16(r + 16 * i);
               activate(r, col0 + 64, v);
@@ -402,7 +448,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             const int col0 = c * 64 + part * kTsCols;
             float v[kTsCols];
             uint32_t r[kTsCols];
-            tmem_load_cols(lane_taddr + d_col + col0, r);
+            load_acc(lane_taddr + d_col + col0, r);
             activate(r, col0, v);
             // last coordinate layer: Linear(Cx -> 1, no bias)
 #pragma unroll
@@ -453,6 +499,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       cur = next;
     }
     if (poisoned && a.status) atomicOr(a.status, (int)B200MD_STATUS_TC_RANGE);
+#if B200MD_TS_SFU_TOKEN
+    if (part == 0) sfu_acquire(tok_mine);   // the peer's last release
+#endif
   }
   tc_fence_before();
   __syncthreads();

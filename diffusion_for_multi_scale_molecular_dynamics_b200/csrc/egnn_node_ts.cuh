@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                                 (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
         int waited = -1;
         for (int c = 0; c < nchunks; ++c) {
-          const int need = (c * 64 + 64 + nh - 1) / nh - 1;
+          const int need = ts_last_group_of_chunk(c, nh);
           if (need > waited) {
             mbar_wait(bars.acc_full(dbuf, need), uses[dbuf] & 1u);
             tc_fence_after();

@@ -16,6 +16,16 @@ constexpr int kTsCols = 64 / kTsParts;            // accumulator columns one epi
 constexpr int kTsEpiWarps = 4 * kTsParts;
 constexpr int kTsThreads = 32 * (2 + kTsEpiWarps);
 
+// Index of the last column group (of `nh` columns each) that accumulator chunk c (columns [64 c, 64 c + 64)) reads.
+// Compares instead of (64 c + 64 + nh - 1) / nh - 1: an integer division is an I2F / MUFU.RCP / F2I chain on the SFU
+// pipe, where it queues behind the SiLU phase of the other epilogue warp (measured: 440 cycles per chunk).
+__device__ __forceinline__ int ts_last_group_of_chunk(int c, int nh) {
+  int need = 0;
+#pragma unroll
+  for (int h = 1; h < kTsNSplit; ++h) need += (c * 64 + 64 > h * nh) ? 1 : 0;
+  return need;
+}
+
 // D[tmem] (+)= A[tmem] * B[smem desc]^T
 // `b_desc_lo`: low word of the K-major SWIZZLE_128B descriptor (desc_lo_sw128); the high word is a constant.
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t idesc,
@@ -119,8 +129,9 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   return r;
 }
 // (silu(x0), silu(x1)) of a packed pair: x / (1 + 2^(-x log2 e)) with the SFU exp2 / reciprocal (about 2 ulp each, far
-// below the 1e-5 parity bound).  Moving the reciprocal to three Newton steps on the FMA pipe halves the SFU load but
-// does not change the launch time: at this point the kernel is limited by the 1000 W power cap, not by a pipe.
+// below the 1e-5 parity bound).  Moving the reciprocal to three Newton steps on the FMA pipe halves the SFU load and
+// saves 2.6 % of the cycles, but the extra FMA work lowers the clock the 1000 W power cap allows (1657 -> 1605 MHz):
+// +-1 % on the launch, within noise, so the SFU version stays.
 __device__ __forceinline__ void silu2(uint64_t x, float& o0, float& o1) {
   float t0, t1, e0, e1, r0, r1;
   unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
@@ -130,6 +141,40 @@ __device__ __forceinline__ void silu2(uint64_t x, float& o0, float& o1) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
   unpack2(mul2(x, pack2(r0, r1)), o0, o1);
+}
+// The same with an SFU "token" dependency: `dep` collects the bits of every reciprocal, so sfu_release(.., dep) cannot
+// be scheduled before the last SFU result exists.
+__device__ __forceinline__ void silu2_dep(uint64_t x, float& o0, float& o1, uint32_t& dep) {
+  float t0, t1, e0, e1, r0, r1;
+  unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), t0, t1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+  dep |= __float_as_uint(r0) | __float_as_uint(r1);
+  unpack2(mul2(x, pack2(r0, r1)), o0, o1);
+}
+// SFU token between the two epilogue warps that share a scheduler (named barriers of 64 threads, strict alternation):
+// both warps are released by the same accumulator barrier and would otherwise run their SiLU phases (SFU-bound) at the
+// same time and their split / store phases (no SFU) at the same time.
+__device__ __forceinline__ void sfu_acquire(uint32_t bar_id) { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
+__device__ __forceinline__ void sfu_arrive(uint32_t bar_id) { asm volatile("bar.arrive %0, 64;" ::"r"(bar_id) : "memory"); }
+// (dep >> 31) + (~dep >> 31) == 1 for every dep, which the assembler cannot see: the arrive stays behind the SFU results
+__device__ __forceinline__ void sfu_release(uint32_t bar_id, uint32_t dep) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 t1, t2;\n"
+      "shr.u32 t1, %1, 31;\n"
+      "not.b32 t2, %1;\n"
+      "shr.u32 t2, t2, 31;\n"
+      "add.u32 t1, t1, t2;\n"
+      "add.u32 t1, t1, %0;\n"
+      "sub.u32 t1, t1, 1;\n"
+      "bar.arrive t1, 64;\n"
+      "}\n" ::"r"(bar_id),
+      "r"(dep)
+      : "memory");
 }
 // shared-memory load by window address (keeps the access an LDS: pointers derived from the aligned dynamic-smem base
 // lose their address space and become generic loads)
