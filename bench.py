@@ -42,12 +42,10 @@ WORKLOADS = {
     "cfg1": ("Si 1x1x1 (8 atoms) EGNN, fully connected, PC Langevin", 8, 5.43, 1, dict(), 4096),
 }
 TOTAL_TIME_STEPS = 1000
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set full`
-# captures (profiles/ncu_full_r01f.txt: egnn_edge_tc_kernel<3xFP16>, 4096 samples; the algorithmic minimum is
-# P + Q + xcur reads, agg read-modify-write and the edge list: about 0.86 GB)
-# dram__bytes_read.sum + dram__bytes_write.sum of one edge-kernel launch (ncu --set full, profiles/ncu_full_r01g.txt /
-# r01f.txt); the algorithmic HBM bytes of a launch are the P / Q / agg rows: 3 x samples x atoms x 1 KB = 805 MB
-NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 875473664 + 251433216, ("cfg2", 4096, "f16x3ts"): 875473664 + 251433216,
+# dram__bytes_read.sum + dram__bytes_write.sum of one edge-kernel launch (ncu --set full at 4096 samples:
+# profiles/ncu_full_r01j.txt for egnn_edge_ts_kernel, ncu_full_r01f.txt for the shared-memory 3xFP16 kernel); the
+# algorithmic HBM bytes of a launch are the P / Q / agg rows: 3 x samples x atoms x 1 KB = 805 MB
+NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 874537728 + 256089600, ("cfg2", 4096, "f16x3ts"): 874537728 + 256089600,
                      ("cfg2", 4096, "f16x3"): 874239488 + 254038784}
 PRODUCTION = dict(n_layers=4, message_n_hidden_dimensions=4, message_hidden_dimensions_size=256,
                   node_n_hidden_dimensions=4, node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4,
