@@ -15,7 +15,7 @@ import json, sys
 k = sys.argv[1]
 try:
     d = json.loads(open(f"gpurun_out/bench_{k}.log").read().strip().splitlines()[-1])
-    print(k, round(d["value"], 2), "structures/s", round(d["ms_per_step"], 1), "ms/step; edge launch", round(d["roofline"]["avg_launch_ms"], 2), "ms", d["clocks"])
+    print(k, round(d["value"], 2), "structures/s", round(d["ms_per_step"], 1), "ms/step; edge launch", round(d["roofline"]["avg_launch_ms"], 2), "ms; node", round(d["roofline"]["class_ms_per_step"]["node"], 2), "ms/step", d["clocks"])
 except Exception as exc:
     print(k, "bench failed", exc)
 PY
