@@ -41,14 +41,23 @@ constexpr int kTsCluster = B200MD_TS_CLUSTER;
 #endif
 constexpr int kTsTokenReleaseAfter = B200MD_TS_TOKEN_RELEASE;
 
+// Weight ring of the edge kernel: one stage fewer than ts_common.cuh's 12, which makes room for the staging tiles of the
+// segmented sum (segment_add below): 32 rows x kTsCols columns of fp32 per epilogue warp.
+#ifndef B200MD_TS_SEG_SMEM
+#define B200MD_TS_SEG_SMEM 1
+#endif
+constexpr int kTsEdgeBStages = B200MD_TS_SEG_SMEM ? 11 : 12;
+constexpr int kTsSegTileBytes = 32 * kTsCols * 4;
+static_assert(!B200MD_TS_SEG_SMEM || kTsCols == 32, "segment_add maps one lane to one column");
 struct TsSmem {
-  uint32_t b, bars, tmem_slot, bias, wr, wlast, dot, total;
+  uint32_t b, seg, bars, tmem_slot, bias, wr, wlast, dot, total;
 };
 __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   TsSmem L;
   uint32_t o = 0;
-  L.b = o; o += kTsBStages * kTsBStageBytes;
-  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit) * 8;
+  L.b = o; o += kTsEdgeBStages * kTsBStageBytes;
+  L.seg = o; o += B200MD_TS_SEG_SMEM ? kTsEpiWarps * kTsSegTileBytes : 0;
+  L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsNSplit) * 8;
   L.tmem_slot = o; o += 16;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
   L.wr = o; o += kMaxN * 4;
@@ -79,14 +88,14 @@ __device__ unsigned g_ts_trace_count;
 struct TsPipe {
   uint32_t s_base, bar0, tmem_base;
   __device__ __forceinline__ uint32_t b_full(uint32_t s) const { return bar0 + 8u * s; }
-  __device__ __forceinline__ uint32_t b_empty(uint32_t s) const { return bar0 + 8u * (kTsBStages + s); }
+  __device__ __forceinline__ uint32_t b_empty(uint32_t s) const { return bar0 + 8u * (kTsEdgeBStages + s); }
   // "columns [part * kTsCols, +kTsCols) of chunk slot `slot` are in TMEM": the 4 lane-quarter warps of that part arrive
   __device__ __forceinline__ uint32_t a_full(uint32_t slot, uint32_t part) const {
-    return bar0 + 8u * (2 * kTsBStages + slot * kTsParts + part);
+    return bar0 + 8u * (2 * kTsEdgeBStages + slot * kTsParts + part);
   }
   // "column group `group` of accumulator buffer `buf` is complete" (groups complete in order)
   __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
-    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
+    return bar0 + 8u * (2 * kTsEdgeBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
   }
 };
 
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   pipe.s_base = smem_u32(smem);
   pipe.bar0 = pipe.s_base + L.bars;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), kTsCluster); }
+    for (int s = 0; s < kTsEdgeBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), kTsCluster); }
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), 4);
     for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(pipe.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
@@ -156,8 +165,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
           const float* src = p.wtc + p.gW[g] + f16_image_offset(p.gK[g], p.gN[g]);
           for (int h = 0; h < kTsNSplit; ++h)
             for (int part = 0; part < 2 * nk; ++part, ++cb) {   // chunk 0 hi, chunk 0 lo, chunk 1 hi, ...
-              const uint32_t s = cb % kTsBStages;
-              mbar_wait(pipe.b_empty(s), ((cb / kTsBStages) & 1u) ^ 1u);
+              const uint32_t s = cb % kTsEdgeBStages;
+              mbar_wait(pipe.b_empty(s), ((cb / kTsEdgeBStages) & 1u) ^ 1u);
               mbar_arrive_expect_tx(pipe.b_full(s), bytes);
               const float* stage_src = src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4);
               if (kTsCluster > 1) {   // this CTA's slice of the stage, delivered to every CTA of the cluster
@@ -191,9 +200,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         for (int h = 0; h < kTsNSplit; ++h) {
           const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
           for (int c = 0; c < nk; ++c) {
-            const uint32_t s1 = cb % kTsBStages, s2 = (cb + 1) % kTsBStages;
-            mbar_wait(pipe.b_full(s1), (cb / kTsBStages) & 1u);
-            mbar_wait(pipe.b_full(s2), ((cb + 1) / kTsBStages) & 1u);
+            const uint32_t s1 = cb % kTsEdgeBStages, s2 = (cb + 1) % kTsEdgeBStages;
+            mbar_wait(pipe.b_full(s1), (cb / kTsEdgeBStages) & 1u);
+            mbar_wait(pipe.b_full(s2), ((cb + 1) / kTsEdgeBStages) & 1u);
             const uint32_t bd1 = desc_lo_sw128(b_ring + s1 * kTsBStageBytes), bd2 = desc_lo_sw128(b_ring + s2 * kTsBStageBytes);
             const uint32_t chunk = mca + (uint32_t)c;
             const uint32_t a_chunk = tmem_base + a_col + (uint32_t)(c * 64);
@@ -258,6 +267,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     // per-tile state of this thread's edge (row of the tile)
     struct Edge {
       int src, dst, seg_start;
+      unsigned tails;   // bit r: row r of this warp ends a segment (and is a real edge)
       bool valid, is_tail;
       float radial;
     };
@@ -273,6 +283,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || ed.src != src_prev);
       ed.seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
       ed.is_tail = (lane == 31) || (ed.src != src_next);
+      ed.tails = __ballot_sync(0xffffffffu, ed.is_tail && ed.valid);
       ed.radial = 0.f;   // coord2radial (models/egnn.py:230-238)
       if (ed.valid)
         for (int d = 0; d < a.D; ++d) {
@@ -281,9 +292,51 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         }
       return ed;
     };
-    // kTsCols columns at once: inclusive segmented scans over the warp's rows (interleaved, so the shuffle latencies
-    // overlap), then one vector reduction per segment tail:  target_row[0 .. kTsCols) += sum over the segment
-    auto segment_add = [&](const Edge& ed, const float (&v)[kTsCols], float* target_row) {
+    // target[src * ld + col0 + (0 .. kTsCols)] += sum of v over each run of equal src inside this warp's 32 rows.
+#if B200MD_TS_SEG_SMEM
+    // Transposed through shared memory: each thread stages its row (XOR-swizzled 16-byte groups, conflict-free both
+    // ways), then lane j walks column j down the 32 rows and issues one coalesced red.global.add per segment tail
+    // (warp-uniform branch on the tails mask).  8 st.shared.v4 + 32 ld.shared per thread instead of 160 shuffles and
+    // 160 selects / adds (the shuffles use the same crossbar as shared memory): the message layer's period drops from
+    // 21.3 k to 13.0 k cycles (other layers: 8.9 k) and the launch from 19.44 to 18.98 ms (A/B on one box).
+    const uint32_t seg_tile = pipe.s_base + L.seg + (uint32_t)(warp - 2) * kTsSegTileBytes;
+    const uint32_t seg_read = seg_tile + (uint32_t)(lane & 3) * 4u;
+    auto segment_add = [&](const Edge& ed, const float (&v)[kTsCols], float* target, int ld, int col0) {
+#pragma unroll
+      for (int g = 0; g < kTsCols / 4; ++g) {
+        const uint32_t at = seg_tile + (uint32_t)lane * (kTsCols * 4) + (uint32_t)((g ^ (lane & 7)) << 4);
+        if (ed.valid) sts128(at, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        else sts128(at, 0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+      // pass 1, branch-free: running sum of column `lane` down the rows, restarted behind every tail, written back in
+      // place.  (A branch per row costs a BSSY / BSYNC pair: 1800 cycles per chunk, measured.  Masked per-segment sums
+      // held in registers instead of the write-back spill and are slower.  What bounds this now is shared-memory
+      // bandwidth: 100 wavefronts per warp and chunk next to the tensor pipe's weight reads, 1300 cycles per chunk.)
+      float t[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = lds32(seg_read + (uint32_t)r * (kTsCols * 4) + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4));
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        acc = (r > 0 && (ed.tails & (1u << (r > 0 ? r - 1 : 0)))) ? t[r] : acc + t[r];
+        sts32(seg_read + (uint32_t)r * (kTsCols * 4) + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4), acc);
+      }
+      // pass 2: one coalesced reduction per tail (two or three per warp at 25 edges per atom)
+      float* const column = target + col0 + lane;
+      for (unsigned m = ed.tails; m != 0; m &= m - 1) {
+        const int r = __ffs(m) - 1;
+        const float sum = lds32(seg_read + (uint32_t)r * (kTsCols * 4) + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4));
+        const int s = __shfl_sync(0xffffffffu, ed.src, r);
+        red_add_f32(column + (int64_t)s * ld, sum);
+      }
+      __syncwarp();
+    };
+#else
+    // inclusive segmented scans over the warp's rows (interleaved, so the shuffle latencies overlap), then one vector
+    // reduction per segment tail
+    auto segment_add = [&](const Edge& ed, const float (&v)[kTsCols], float* target, int ld, int col0) {
+      float* target_row = target + (int64_t)ed.src * ld + col0;
       float sum[kTsCols];
 #pragma unroll
       for (int j = 0; j < kTsCols; ++j) sum[j] = ed.valid ? v[j] : 0.f;
@@ -301,6 +354,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         for (int j = 0; j < kTsCols / 4; ++j) red_add_v4(target_row + 4 * j, sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
       }
     };
+#endif
     // chunk c of the first activation of a tile: silu(P[src] + Q[dst] + radial * w_r) -> A operand at a_col
     auto prefetch_first = [&](const Edge& ed, int c) {
 #ifndef B200MD_TS_NO_PREFETCH
@@ -330,7 +384,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #pragma unroll
         for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
       }
-      if (a.n_msg == 0) segment_add(ed, v, a.agg + (int64_t)ed.src * M + col0);  // no hidden layer: this IS the message
+      if (a.n_msg == 0) segment_add(ed, v, a.agg, M, col0);  // no hidden layer: this IS the message
       uint32_t w[kTsCols];
       split_hi_lo(v, w);
       publish(a_col + (uint32_t)col0, w);
@@ -430,7 +484,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             TS_TRACE(9, g * 16 + c);
             publish(d_col + (uint32_t)col0, w);
             TS_TRACE(6, g * 16 + c);
-            if (is_message) segment_add(cur, v, a.agg + (int64_t)cur.src * M + col0);  // agg[src] += m (models/egnn.py:178-181)
+            if (is_message) {
+              TS_TRACE(16, g * 16 + c);
+              segment_add(cur, v, a.agg, M, col0);  // agg[src] += m (models/egnn.py:178-181)
+              TS_TRACE(17, g * 16 + c);
+            }
             if (more) {
               TS_TRACE(12, g * 16 + c);
 #if B200MD_TS_SFU_TOKEN

@@ -186,6 +186,20 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
+__device__ __forceinline__ void red_add_f32(float* addr, float x) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(x) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(x) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ts_epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(kTsEpiWarps * 32) : "memory"); }
