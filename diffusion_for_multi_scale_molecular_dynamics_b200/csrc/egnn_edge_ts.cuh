@@ -46,7 +46,10 @@ constexpr int kTsTokenReleaseAfter = B200MD_TS_TOKEN_RELEASE;
 #ifndef B200MD_TS_SEG_SMEM
 #define B200MD_TS_SEG_SMEM 1
 #endif
-constexpr int kTsEdgeBStages = B200MD_TS_SEG_SMEM ? 11 : 12;
+#ifndef B200MD_TS_EDGE_STAGES
+#define B200MD_TS_EDGE_STAGES 11
+#endif
+constexpr int kTsEdgeBStages = B200MD_TS_SEG_SMEM ? B200MD_TS_EDGE_STAGES : 12;
 constexpr int kTsSegTileBytes = 32 * kTsCols * 4;
 static_assert(!B200MD_TS_SEG_SMEM || kTsCols == 32, "segment_add maps one lane to one column");
 struct TsSmem {
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #endif
     // chunk c of the first activation of a tile: silu(P[src] + Q[dst] + radial * w_r) -> A operand at a_col
     auto prefetch_first = [&](const Edge& ed, int c) {
-#ifndef B200MD_TS_NO_PREFETCH
+#ifdef B200MD_TS_PREFETCH   // off: with 227 KB of shared memory in use there is no L1 left to prefetch into (A/B: -1 %)
       if (ed.valid) {
         const float* pp = a.P + (int64_t)ed.src * M + c * 64 + part * kTsCols;
         const float* qq = a.Q + (int64_t)ed.dst * M + c * 64 + part * kTsCols;
