@@ -12,7 +12,8 @@ rows = list(csv.reader(raw.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
 b = starts[0]
 header = rows[b + 1]
-body = [r for r in rows[b + 2:] if len(r) == len(header)]
+end = starts[1] if len(starts) > 1 else len(rows)
+body = [r for r in rows[b + 2:end] if len(r) == len(header) and r != header]
 si = header.index("Warp Stall Sampling (All Samples)")
 srci = header.index("Source")
 ie = header.index("Instructions Executed")
