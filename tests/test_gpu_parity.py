@@ -339,7 +339,9 @@ def test_egnn_forward_production_width_against_oracle(cuda_device, num_atom_type
     dict(message_hidden_dimensions_size=128, coordinate_hidden_dimensions_size=192, message_n_hidden_dimensions=2,
          coordinate_n_hidden_dimensions=2, node_hidden_dimensions_size=64, node_n_hidden_dimensions=3, n_layers=2,
          normalize=True, message_agg="sum"),
-], ids=["96x160-norm-tanh-sum", "32-no-hidden-message", "256to64-fully-connected", "128x192x64"])
+    dict(message_hidden_dimensions_size=64, coordinate_hidden_dimensions_size=128, message_n_hidden_dimensions=0,
+         coordinate_n_hidden_dimensions=1, node_hidden_dimensions_size=64, n_layers=2, coords_agg="sum"),
+], ids=["96x160-norm-tanh-sum", "32-no-hidden-message", "256to64-fully-connected", "128x192x64", "64-no-hidden-message"])
 @pytest.mark.parametrize("impl", TC_IMPLS, ids=TC_IDS)
 def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp, impl):
     """The tensor-core kernels over their whole supported envelope: widths that are multiples of 32 (3xTF32) or 64
@@ -355,6 +357,17 @@ def test_tcgen05_edge_kernel_shapes_against_oracle(cuda_device, hp, impl):
         return
     net = run_against_oracle(cuda_device, full, 40, 5, 7.0, impl, seed=8)
     assert "tcgen05" in net.last_edge_kernel_name()
+
+
+@pytest.mark.parametrize("N,B", [(8, 37), (3, 50), (2, 129)], ids=["8-atoms", "3-atoms", "2-atoms"])
+def test_ts_edge_kernel_short_segments(cuda_device, N, B):
+    """Fully connected small cells: N - 1 edges per source atom, so every warp of the edge kernel holds many segment
+    tails (and the last tile is ragged) -- the shared-memory segmented sum of the messages at its other extreme."""
+    hp = dict(num_atom_types=1, edges="fully_connected", message_hidden_dimensions_size=128,
+              coordinate_hidden_dimensions_size=64, node_hidden_dimensions_size=64, message_n_hidden_dimensions=2,
+              coordinate_n_hidden_dimensions=1, n_layers=2)
+    net = run_against_oracle(cuda_device, hp, N, B, 5.43, _cabi.IMPL_TCGEN05_F16X3_TS, seed=11)
+    assert "ts" in net.last_edge_kernel_name()
 
 
 @pytest.mark.parametrize("impl", [_cabi.IMPL_TCGEN05_F16X3, _cabi.IMPL_TCGEN05_F16X3_TS], ids=["f16x3", "f16x3ts"])
