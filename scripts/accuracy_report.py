@@ -47,7 +47,8 @@ def rel(u, v):
 
 
 report = {"oracle_fp32_vs_fp64": {"score": rel(s32, s64), "logits": rel(l32, l64)}}
-for name, impl in (("ffma", _cabi.IMPL_FFMA), ("tf32x3", _cabi.IMPL_TCGEN05), ("f16x3", _cabi.IMPL_TCGEN05_F16X3)):
+for name, impl in (("ffma", _cabi.IMPL_FFMA), ("tf32x3", _cabi.IMPL_TCGEN05), ("f16x3", _cabi.IMPL_TCGEN05_F16X3),
+                   ("f16x3ts", _cabi.IMPL_TCGEN05_F16X3_TS)):
     net.kernel_impl = impl
     out = net(batch, conditional=False)
     report[name] = {"score_vs_fp32_oracle": rel(out.X.cpu(), s32), "logits_vs_fp32_oracle": rel(out.A.cpu(), l32),
