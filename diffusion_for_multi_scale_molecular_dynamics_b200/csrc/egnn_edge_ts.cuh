@@ -8,11 +8,11 @@
 // ring), and the tensor pipe reads only B from shared memory.
 //
 // Because A(g+1) stays in TMEM for the whole GEMM, the MMA order is column-group-major: the accumulator is computed
-// in kTsNSplit groups of N / kTsNSplit columns, the first group over all K chunks as the epilogue delivers them, the
-// others back to back.  With four groups (64 columns = one K chunk of the next layer each) the epilogue converts group
-// c while the tensor pipe computes group c + 1: the two run in lock-step instead of taking turns.  At the end of a
-// tile the columns of the last accumulator are reused the same way for the NEXT tile's first activation, so the
-// tensor pipe never drains between tiles.
+// in kTsEdgeNSplit groups of N / kTsEdgeNSplit columns, the first group over all K chunks as the epilogue delivers
+// them, the others back to back, and the epilogue of layer g + 1 starts on a group as soon as it is complete.  (One
+// group is the default now; two and four were measured, see kTsEdgeNSplit below.)  At the end of a tile the columns of
+// the last accumulator are reused the same way for the NEXT tile's first activation, so the tensor pipe never drains
+// between tiles.
 //   GEMM index n (running over tiles): D = buffer n & 1, A = buffer (n & 1) ^ 1 (2 x 256 columns = all of TMEM).
 //
 // Warps (10): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue: two per TMEM lane quarter,
@@ -41,15 +41,23 @@ constexpr int kTsCluster = B200MD_TS_CLUSTER;
 #endif
 constexpr int kTsTokenReleaseAfter = B200MD_TS_TOKEN_RELEASE;
 
-// Weight ring of the edge kernel: one stage fewer than ts_common.cuh's 12, which makes room for the staging tiles of the
-// segmented sum (segment_add below): 32 rows x kTsCols columns of fp32 per epilogue warp.
+// Column groups and weight ring of the edge kernel (the node kernel keeps ts_common.cuh's two groups and 12 stages).
+// One group = whole-width MMAs (N = 256): 139 cycles each against 2 x 75 for two halves, half as many instructions
+// and weight stages; it lost to two groups while the epilogue was the bound (20.4 vs 20.15 ms) and wins now that the
+// epilogue is shorter (A/B on one box: 19.03 -> 18.42 ms per launch).  The ring leaves room for the staging tiles of
+// the segmented sum (segment_add below): 32 rows x kTsCols columns of fp32 per epilogue warp.
 #ifndef B200MD_TS_SEG_SMEM
 #define B200MD_TS_SEG_SMEM 1
 #endif
-#ifndef B200MD_TS_EDGE_STAGES
-#define B200MD_TS_EDGE_STAGES 11
+#ifndef B200MD_TS_EDGE_NSPLIT
+#define B200MD_TS_EDGE_NSPLIT 1
 #endif
-constexpr int kTsEdgeBStages = B200MD_TS_SEG_SMEM ? B200MD_TS_EDGE_STAGES : 12;
+constexpr int kTsEdgeNSplit = B200MD_TS_EDGE_NSPLIT;
+constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes;
+#ifndef B200MD_TS_EDGE_STAGES
+#define B200MD_TS_EDGE_STAGES ((B200MD_TS_SEG_SMEM ? 11 : 12) * B200MD_TS_EDGE_NSPLIT / 2)
+#endif
+constexpr int kTsEdgeBStages = B200MD_TS_EDGE_STAGES;
 constexpr int kTsSegTileBytes = 32 * kTsCols * 4;
 static_assert(!B200MD_TS_SEG_SMEM || kTsCols == 32, "segment_add maps one lane to one column");
 struct TsSmem {
@@ -58,9 +66,9 @@ struct TsSmem {
 __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   TsSmem L;
   uint32_t o = 0;
-  L.b = o; o += kTsEdgeBStages * kTsBStageBytes;
+  L.b = o; o += kTsEdgeBStages * kTsEdgeBStageBytes;
   L.seg = o; o += B200MD_TS_SEG_SMEM ? kTsEpiWarps * kTsSegTileBytes : 0;
-  L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsNSplit) * 8;
+  L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsEdgeNSplit) * 8;
   L.tmem_slot = o; o += 16;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
   L.wr = o; o += kMaxN * 4;
@@ -98,7 +106,7 @@ struct TsPipe {
   }
   // "column group `group` of accumulator buffer `buf` is complete" (groups complete in order)
   __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
-    return bar0 + 8u * (2 * kTsEdgeBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
+    return bar0 + 8u * (2 * kTsEdgeBStages + kTsSlots * kTsParts + buf * kTsEdgeNSplit + group);
   }
 };
 
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     for (int s = 0; s < kTsEdgeBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), kTsCluster); }
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), 4);
-    for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(pipe.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
+    for (int s = 0; s < 2 * kTsEdgeNSplit; ++s) mbar_init(pipe.acc_full(s / kTsEdgeNSplit, s % kTsEdgeNSplit), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(pipe.s_base + L.tmem_slot, kTmemCols);
@@ -162,11 +170,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       uint32_t cb = 0;
       for (int it = 0; it < n_iterations; ++it)
         for (int g = 0; g < p.n_gemms; ++g) {
-          const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsNSplit;
+          const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsEdgeNSplit;
           const uint32_t bytes = (uint32_t)nh * kRowBytes;
           const int64_t part_floats = (int64_t)p.gN[g] * (kRowBytes / 4);
           const float* src = p.wtc + p.gW[g] + f16_image_offset(p.gK[g], p.gN[g]);
-          for (int h = 0; h < kTsNSplit; ++h)
+          for (int h = 0; h < kTsEdgeNSplit; ++h)
             for (int part = 0; part < 2 * nk; ++part, ++cb) {   // chunk 0 hi, chunk 0 lo, chunk 1 hi, ...
               const uint32_t s = cb % kTsEdgeBStages;
               mbar_wait(pipe.b_empty(s), ((cb / kTsEdgeBStages) & 1u) ^ 1u);
@@ -174,10 +182,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               const float* stage_src = src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4);
               if (kTsCluster > 1) {   // this CTA's slice of the stage, delivered to every CTA of the cluster
                 const uint32_t slice = bytes / kTsCluster;
-                bulk_g2s_multicast(pipe.s_base + L.b + s * kTsBStageBytes + cta_rank * slice, stage_src + cta_rank * (slice / 4),
+                bulk_g2s_multicast(pipe.s_base + L.b + s * kTsEdgeBStageBytes + cta_rank * slice, stage_src + cta_rank * (slice / 4),
                                    slice, pipe.b_full(s), (uint16_t)((1u << kTsCluster) - 1u));
               } else {
-                bulk_g2s(pipe.s_base + L.b + s * kTsBStageBytes, stage_src, bytes, pipe.b_full(s));
+                bulk_g2s(pipe.s_base + L.b + s * kTsEdgeBStageBytes, stage_src, bytes, pipe.b_full(s));
               }
             }
         }
@@ -197,16 +205,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #ifdef B200MD_TS_TRACE
         trace_on = (blockIdx.x == 0 && lane == 0 && it >= 3 && it < 5);
 #endif
-        const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsNSplit;
+        const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsEdgeNSplit;
         const uint32_t idesc = make_idesc(nh, 0u);
         const uint32_t d_col = (mgc & 1u) * kMaxN, a_col = d_col ^ kMaxN;
-        for (int h = 0; h < kTsNSplit; ++h) {
+        for (int h = 0; h < kTsEdgeNSplit; ++h) {
           const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
           for (int c = 0; c < nk; ++c) {
             const uint32_t s1 = cb % kTsEdgeBStages, s2 = (cb + 1) % kTsEdgeBStages;
             mbar_wait(pipe.b_full(s1), (cb / kTsEdgeBStages) & 1u);
             mbar_wait(pipe.b_full(s2), ((cb + 1) / kTsEdgeBStages) & 1u);
-            const uint32_t bd1 = desc_lo_sw128(b_ring + s1 * kTsBStageBytes), bd2 = desc_lo_sw128(b_ring + s2 * kTsBStageBytes);
+            const uint32_t bd1 = desc_lo_sw128(b_ring + s1 * kTsEdgeBStageBytes), bd2 = desc_lo_sw128(b_ring + s2 * kTsEdgeBStageBytes);
             const uint32_t chunk = mca + (uint32_t)c;
             const uint32_t a_chunk = tmem_base + a_col + (uint32_t)(c * 64);
 #pragma unroll
@@ -417,7 +425,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         const bool is_message = (g == a.n_msg - 1);
         const bool is_last = (g == p.n_gemms - 1);
         const uint32_t d_col = (gc & 1u) * kMaxN;
-        const int nchunks = p.gN[g] / 64, nh = p.gN[g] / kTsNSplit;
+        const int nchunks = p.gN[g] / 64, nh = p.gN[g] / kTsEdgeNSplit;
         const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
         if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
           next = load_edge(it + 1);
@@ -425,7 +433,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         }
         int waited = -1;
         auto wait_for_chunk = [&](int c) {
-          const int need = ts_last_group_of_chunk(c, nh);
+          const int need = ts_last_group_of_chunk<kTsEdgeNSplit>(c, nh);
           if (need > waited) {
             TS_TRACE(1, g * 16 + c);
             mbar_wait(pipe.acc_full(gc & 1u, need), (gc >> 1) & 1u);

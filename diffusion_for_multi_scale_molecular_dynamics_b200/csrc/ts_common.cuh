@@ -19,10 +19,11 @@ constexpr int kTsThreads = 32 * (2 + kTsEpiWarps);
 // Index of the last column group (of `nh` columns each) that accumulator chunk c (columns [64 c, 64 c + 64)) reads.
 // Compares instead of (64 c + 64 + nh - 1) / nh - 1: an integer division is an I2F / MUFU.RCP / F2I chain on the SFU
 // pipe, where it queues behind the SiLU phase of the other epilogue warp (measured: 440 cycles per chunk).
+template <int NSPLIT = kTsNSplit>
 __device__ __forceinline__ int ts_last_group_of_chunk(int c, int nh) {
   int need = 0;
 #pragma unroll
-  for (int h = 1; h < kTsNSplit; ++h) need += (c * 64 + 64 > h * nh) ? 1 : 0;
+  for (int h = 1; h < NSPLIT; ++h) need += (c * 64 + 64 > h * nh) ? 1 : 0;
   return need;
 }
 
