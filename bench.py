@@ -43,9 +43,9 @@ WORKLOADS = {
 }
 TOTAL_TIME_STEPS = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum of one edge-kernel launch (ncu --set full at 4096 samples:
-# profiles/ncu_full_r01k.txt for egnn_edge_ts_kernel, ncu_full_r01f.txt for the shared-memory 3xFP16 kernel); the
+# profiles/ncu_full_r01l.txt for egnn_edge_ts_kernel, ncu_full_r01f.txt for the shared-memory 3xFP16 kernel); the
 # algorithmic HBM bytes of a launch are the P / Q / agg rows: 3 x samples x atoms x 1 KB = 805 MB
-NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 873745152 + 255077632, ("cfg2", 4096, "f16x3ts"): 873745152 + 255077632,
+NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 874701312 + 253051648, ("cfg2", 4096, "f16x3ts"): 874701312 + 253051648,
                      ("cfg2", 4096, "f16x3"): 874239488 + 254038784}
 PRODUCTION = dict(n_layers=4, message_n_hidden_dimensions=4, message_hidden_dimensions_size=256,
                   node_n_hidden_dimensions=4, node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4,
