@@ -41,12 +41,13 @@ STATUS_MESSAGES = {
     STATUS_BAD_LOGITS: "Logits are pathological: the probabilities do not sum to one.",
     STATUS_SIGMA_OUT_OF_RANGE: "All values of sigma should be larger than zero.",
     STATUS_TC_RANGE: "An activation exceeded the fp16 range of the 3xFP16 tensor-core kernels; set "
-    "kernel_impl = IMPL_TCGEN05 (3xTF32) for this network.",
+    "kernel_impl = IMPL_TCGEN05 (3xTF32) for this network (kernel_impl = IMPL_AUTO does so by itself).",
 }
 
 DRAW_COORD_NORMAL, DRAW_GUMBEL, DRAW_BINARY, DRAW_LATTICE_NORMAL = 0, 1, 2, 3
 DRAW_INIT_UNIFORM, DRAW_REPAINT_NORMAL, DRAW_REPAINT_UNIFORM, DRAW_REPAINT_INIT = 4, 5, 6, 7
 DRAW_LATTICE_NORMAL_SECOND = 8  # the corrector's second lattice draw (reference langevin_generator.py:771-777)
+DRAW_INIT_LATTICE = 9  # the starting lattice L_T: its own key, (step 0, DRAW_LATTICE_NORMAL) is the last predictor's draw
 
 ATOM_GREEDY, ATOM_ONE_TRANSITION, ATOM_LAST_STEP = 1, 2, 4
 GRAPH_UNIQUE_PAIRS, GRAPH_PER_IMAGE = 0, 1
@@ -236,13 +237,23 @@ def as_i64(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.int64).contiguous()
 
 
-def raise_on_status(status: torch.Tensor, error=AssertionError) -> None:
-    """Read the device status word (one host sync) and raise like the reference's asserts would."""
-    word = int(status.item())
+def status_word(status: Optional[torch.Tensor]) -> int:
+    """The device status word as a host integer (one host sync)."""
+    return 0 if status is None else int(status.item())
+
+
+def raise_for_word(word: int, status: Optional[torch.Tensor], error=AssertionError) -> None:
+    """Turn a non-zero status word into the reference's assertion text; the device word is cleared first."""
     if word:
         messages = [text for bit, text in STATUS_MESSAGES.items() if word & bit]
-        status.zero_()
+        if status is not None:
+            status.zero_()
         raise error(" ".join(messages) if messages else f"device status {word}")
+
+
+def raise_on_status(status: torch.Tensor, error=AssertionError) -> None:
+    """Read the device status word (one host sync) and raise like the reference's asserts would."""
+    raise_for_word(status_word(status), status, error)
 
 
 KERNEL_CLASSES = ("graph", "node", "edge", "update", "other")

@@ -33,6 +33,21 @@ struct ProfileScope {
 
 static inline cudaStream_t as_stream(b200md_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) and the SM count belong to a DEVICE, not to
+// the process: a "done once" flag must be kept per device ordinal.  `PerDeviceOnce once; if (once.needed()) { ...set...;
+// once.done(); }` -- setting twice from two threads is harmless, skipping a device is not.
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+struct PerDeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  volatile bool flag[kMaxDevices] = {};
+  bool needed() const { const int d = current_device(); return d < 0 || d >= kMaxDevices || !flag[d]; }
+  void done() { const int d = current_device(); if (d >= 0 && d < kMaxDevices) flag[d] = true; }
+};
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------

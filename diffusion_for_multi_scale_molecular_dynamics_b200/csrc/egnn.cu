@@ -536,13 +536,13 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
                       float sigma_scalar, int64_t B, int32_t N, int mask_logit, float* logits_out,
                       float* score_out, const EgnnWorkspace& ws, int64_t edge_capacity, int32_t* status,
                       int impl, cudaStream_t st) {
-  static bool attrs_set = false;
-  if (!attrs_set) {
+  static PerDeviceOnce attrs;
+  if (attrs.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(egnn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node_smem_bytes());
     cudaError_t e2 = cudaFuncSetAttribute(egnn_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes());
     if (e1 != cudaSuccess) return set_cuda_error(e1);
     if (e2 != cudaSuccess) return set_cuda_error(e2);
-    attrs_set = true;
+    attrs.done();
   }
   // B200MD_IMPL_TCGEN05: 3xTF32 tensor-core kernels (any widths that are multiples of 32); B200MD_IMPL_TCGEN05_F16X3:
   // 3xFP16 (multiples of 64), A operand through shared memory; B200MD_IMPL_TCGEN05_F16X3_TS: 3xFP16 with the edge

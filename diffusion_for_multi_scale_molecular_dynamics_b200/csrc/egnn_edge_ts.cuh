@@ -61,7 +61,7 @@ constexpr int kTsEdgeBStages = B200MD_TS_EDGE_STAGES;
 constexpr int kTsSegTileBytes = 32 * kTsCols * 4;
 static_assert(!B200MD_TS_SEG_SMEM || kTsCols == 32, "segment_add maps one lane to one column");
 struct TsSmem {
-  uint32_t b, seg, bars, tmem_slot, bias, wr, wlast, dot, total;
+  uint32_t b, seg, bars, tmem_slot, bias, scale, wr, wlast, dot, total;
 };
 __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   TsSmem L;
@@ -71,6 +71,7 @@ __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsEdgeNSplit) * 8;
   L.tmem_slot = o; o += 16;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
+  L.scale = o; o += 16 * 4;   // 2^-s of each GEMM's fp16 weight image (tc_common.cuh)
   L.wr = o; o += kMaxN * 4;
   L.wlast = o; o += kMaxN * 4;
   L.dot = o; o += 2 * kTsParts * kTileM * 4;   // [tile parity][part][row]
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     s_wr[t] = (t < M) ? p.packed[a.msg_wr + t] : 0.f;
     s_wlast[t] = (t < p.gN[p.n_gemms - 1]) ? p.packed[a.coord_last_w + t] : 0.f;
   }
+  if (threadIdx.x < p.n_gemms)
+    reinterpret_cast<float*>(smem + L.scale)[threadIdx.x] = p.wtc[p.gW[threadIdx.x] + weight_unscale_offset(p.gK[threadIdx.x], p.gN[threadIdx.x])];
   TsPipe pipe;
   pipe.s_base = smem_u32(smem);
   pipe.bar0 = pipe.s_base + L.bars;
@@ -427,6 +430,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         const uint32_t d_col = (gc & 1u) * kMaxN;
         const int nchunks = p.gN[g] / 64, nh = p.gN[g] / kTsEdgeNSplit;
         const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
+        const float unscale = lds32(pipe.s_base + L.scale + (uint32_t)g * 4u);   // accumulator = 2^s x product
+        const uint64_t unscale2 = pack2(unscale, unscale);
         if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
           next = load_edge(it + 1);
           prefetch_first(next, 0);
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             TS_TRACE(2, g * 16 + c);
           }
         };
-        // v = silu(accumulator + bias)
+        // v = silu(accumulator * 2^-s + bias)
         auto activate = [&](const uint32_t (&r)[kTsCols], int col0, float (&v)[kTsCols]) {
           TS_TRACE(4, col0);
 #if B200MD_TS_SFU_TOKEN
@@ -450,16 +455,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #pragma unroll
           for (int j = 0; j < kTsCols / 4; ++j) {
             const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-            silu2_dep(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1], dep);
-            silu2_dep(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3], dep);
+            silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1], dep);
+            silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3], dep);
             if (j == kTsTokenReleaseAfter) sfu_release(tok_peer, dep);
           }
 #else
 #pragma unroll
           for (int j = 0; j < kTsCols / 4; ++j) {
             const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-            silu2(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
-            silu2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
+            silu2(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
+            silu2(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
           }
 #endif
           TS_TRACE(5, col0);

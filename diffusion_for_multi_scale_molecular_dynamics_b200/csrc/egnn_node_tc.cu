@@ -33,12 +33,13 @@ struct NodeTcArgs {
 };
 
 struct NodeSmem {
-  uint32_t bias, total;
+  uint32_t bias, scale, total;
 };
 __host__ __device__ inline NodeSmem node_smem(int n_gemms) {
   NodeSmem L;
   uint32_t o = pipe_smem().end;
   L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
+  L.scale = o; o += 16 * 4;   // 2^-s of each GEMM's weight image (1 in the TF32 mode)
   L.total = o;
   return L;
 }
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
   const Program& p = a.prog;
   const NodeSmem L = node_smem(p.n_gemms);
   float* s_bias = reinterpret_cast<float*>(smem + L.bias);
+  float* s_scale = reinterpret_cast<float*>(smem + L.scale);
   const float* Wp = p.packed;
   constexpr int kChunk = Mode<PREC>::kChunk, kVals = Mode<PREC>::kVals;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
     const int g = t / kMaxN, n = t - g * kMaxN;
     s_bias[t] = (n < p.gN[g] && p.gB[g] >= 0) ? Wp[p.gB[g] + n] : 0.f;
   }
+  if (threadIdx.x < p.n_gemms)
+    s_scale[threadIdx.x] = (PREC == kF16x3) ? p.wtc[p.gW[threadIdx.x] + weight_unscale_offset(p.gK[threadIdx.x], p.gN[threadIdx.x])] : 1.0f;
   Pipe<PREC> pipe;
   pipe.setup(smem);
   const TileSchedule sched = make_schedule(n_tiles);
@@ -183,17 +187,18 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
           const bool last = (g == a.n_update - 1);
           const uint32_t acc_col = pipe.wait_accumulator();
           const float* bias = s_bias + g * kMaxN;
+          const float unscale = s_scale[g];
           for (int c = 0; c < p.gN[g] / kChunk; ++c) {
             const int col0 = c * kChunk + hh * kVals;
             float v[kVals];
             tmem_ld<kVals>(lane_taddr + acc_col + col0, v);
             if (!last) {
 #pragma unroll
-              for (int j = 0; j < kVals; ++j) v[j] = silu_fast(v[j] + bias[col0 + j]);
+              for (int j = 0; j < kVals; ++j) v[j] = silu_fast(fmaf(v[j], unscale, bias[col0 + j]));
               vmax = fmaxf(vmax, pipe.push_chunk(row, hh, lane, v));
             } else {
 #pragma unroll
-              for (int j = 0; j < kVals; ++j) v[j] += bias[col0 + j];
+              for (int j = 0; j < kVals; ++j) v[j] = fmaf(v[j], unscale, bias[col0 + j]);
               if (valid) {
                 if (a.residual) {
                   float old[kVals];
@@ -227,13 +232,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
           const int g = a.n_update + which;
           const uint32_t acc_col = pipe.wait_accumulator();
           const float* bias = s_bias + g * kMaxN;
+          const float unscale = s_scale[g];
           float* out = which == 0 ? a.P : a.Q;
           for (int c = 0; c < p.gN[g] / kChunk; ++c) {
             const int col0 = c * kChunk + hh * kVals;
             float v[kVals];
             tmem_ld<kVals>(lane_taddr + acc_col + col0, v);
 #pragma unroll
-            for (int j = 0; j < kVals; ++j) v[j] += bias[col0 + j];
+            for (int j = 0; j < kVals; ++j) v[j] = fmaf(v[j], unscale, bias[col0 + j]);
             if (valid) store_row<kVals>(out + node * M + col0, v);
           }
           tc_fence_before();
@@ -287,8 +293,8 @@ bool tc_node_supported(const b200md_egnn_config& cfg, int precision) {
 
 // per layer: [W_a (H -> M)] [W_b (H -> M)] [node_w0 (H+M -> H)] [node hidden ...] [node last (H -> H)]
 int64_t tc_node_packed_floats(const b200md_egnn_config& cfg) {
-  const int64_t H = cfg.node_hidden, M = cfg.message_hidden;
-  return 3 * (2 * H * M + (H + M) * H + cfg.node_n_hidden * H * H + H * H);
+  const int H = cfg.node_hidden, M = cfg.message_hidden;
+  return 2 * weight_image_floats(H, M) + weight_image_floats(H + M, H) + (cfg.node_n_hidden + 1) * weight_image_floats(H, H);
 }
 
 struct NodeImage {
@@ -369,23 +375,24 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
     t.wtc = p.wtc; t.packed = packed;
     int n = 0;
     auto f16 = [&](int64_t image, int K, int N) { return image + f16_image_offset(K, N); };
+    auto uns = [&](int64_t image, int K, int N) { return image + weight_unscale_offset(K, N); };
     if (call.update_layer >= 0) {
       const EgnnLayerOffsets& Lo = lay.layer[call.update_layer];
       const int64_t base = (int64_t)call.update_layer * lay.tc_node_stride;
       const int64_t w0 = f16(base + im.w0, H + M, H);
-      t.g[n] = NodeTsGemm{M, H, kNodeChainAddU, 1, 0, 0, w0 + (int64_t)(H / 64) * 2 * H * 32, -1, nullptr}; ++n;
+      t.g[n] = NodeTsGemm{M, H, kNodeChainAddU, 1, 0, 0, w0 + (int64_t)(H / 64) * 2 * H * 32, uns(base + im.w0, H + M, H), -1, nullptr}; ++n;
       for (int i = 0; i < cfg.node_n_hidden; ++i) {
-        t.g[n] = NodeTsGemm{H, H, kNodeChain, 1, 0, 0, f16(base + im.hidden + i * weight_image_floats(H, H), H, H),
-                            Lo.node_hidden_b + (int64_t)i * H, nullptr}; ++n;
+        const int64_t image = base + im.hidden + i * weight_image_floats(H, H);
+        t.g[n] = NodeTsGemm{H, H, kNodeChain, 1, 0, 0, f16(image, H, H), uns(image, H, H), Lo.node_hidden_b + (int64_t)i * H, nullptr}; ++n;
       }
-      t.g[n] = NodeTsGemm{H, H, kNodeChainLast, 1, 0, 0, f16(base + im.last, H, H), Lo.node_last_b, nullptr}; ++n;
+      t.g[n] = NodeTsGemm{H, H, kNodeChainLast, 1, 0, 0, f16(base + im.last, H, H), uns(base + im.last, H, H), Lo.node_last_b, nullptr}; ++n;
     }
     if (call.pq_layer >= 0) {
       const EgnnLayerOffsets& Lo = lay.layer[call.pq_layer];
       const int64_t base = (int64_t)call.pq_layer * lay.tc_node_stride;
-      t.g[n] = NodeTsGemm{H, M, kNodeOut, 1, 0, 1, f16(base + im.wa, H, M), Lo.msg_b0, call.ws->P}; ++n;
-      t.g[n] = NodeTsGemm{H, M, kNodeOut, 0, 1, 1, f16(base + im.wb, H, M), -1, call.ws->Q}; ++n;
-      t.g[n] = NodeTsGemm{H, H, kNodeOut, 0, 1, 0, f16(base + im.w0, H + M, H), Lo.node_b0, call.ws->U}; ++n;
+      t.g[n] = NodeTsGemm{H, M, kNodeOut, 1, 0, 1, f16(base + im.wa, H, M), uns(base + im.wa, H, M), Lo.msg_b0, call.ws->P}; ++n;
+      t.g[n] = NodeTsGemm{H, M, kNodeOut, 0, 1, 1, f16(base + im.wb, H, M), uns(base + im.wb, H, M), -1, call.ws->Q}; ++n;
+      t.g[n] = NodeTsGemm{H, H, kNodeOut, 0, 1, 0, f16(base + im.w0, H + M, H), uns(base + im.w0, H + M, H), Lo.node_b0, call.ws->U}; ++n;
     }
     t.n_gemms = n;
     t.do_embed = call.embed; t.do_update = call.update_layer >= 0; t.do_readout = call.readout;
@@ -399,11 +406,11 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
     t.bloch = lay.bloch; t.proj = lay.proj; t.embed_w = lay.embed_w; t.embed_b = lay.embed_b;
     t.readout_w = lay.readout_w; t.readout_b = lay.readout_b;
     const size_t ts_bytes = node_ts_smem(n).total + 1024;
-    static bool ts_attr_set = false;
-    if (!ts_attr_set) {
+    static PerDeviceOnce ts_attr_set;
+    if (ts_attr_set.needed()) {
       cudaError_t e0 = cudaFuncSetAttribute(egnn_node_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e0 != cudaSuccess) return set_cuda_error(e0);
-      ts_attr_set = true;
+      ts_attr_set.done();
     }
     const int64_t tiles = ceil_div64(call.n_nodes, kTileM);
     const unsigned grid = (unsigned)(tiles < 1 ? 1 : (tiles > tc_sm_count() ? tc_sm_count() : tiles));
@@ -412,13 +419,13 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
     return B200MD_OK;
   }
   const size_t smem = node_smem(p.n_gemms).total + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(egnn_node_tc_kernel<kTf32x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaError_t e2 = cudaFuncSetAttribute(egnn_node_tc_kernel<kF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e1 != cudaSuccess) return set_cuda_error(e1);
     if (e2 != cudaSuccess) return set_cuda_error(e2);
-    attr_set = true;
+    attr_set.done();
   }
   const int64_t n_tiles = ceil_div64(call.n_nodes, kTileM);
   {

@@ -33,6 +33,7 @@ struct NodeTsGemm {
   int wait_d_free;      // the accumulator buffer still holds the previous output: wait until the epilogue drained it
   int signal_d_free;    // ... and the epilogue says so after draining this one
   int64_t w16;          // offset (floats) in wtc of the fp16 image of the first K chunk
+  int64_t unscale;      // offset in wtc of 2^-s: the image holds 2^s w (tc_common.cuh), the epilogue multiplies it back
   int64_t bias;         // offset in packed, or -1
   float* out;           // kNodeOut: destination [n_nodes, N]
 };
@@ -57,7 +58,7 @@ struct NodeTsArgs {
 constexpr int kNodeMaxClasses = 8;
 
 struct NodeTsSmem {
-  uint32_t b, bars, tmem_slot, bias, readout, logits, total;
+  uint32_t b, bars, tmem_slot, bias, scale, readout, logits, total;
 };
 __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   NodeTsSmem L;
@@ -67,6 +68,7 @@ __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   L.tmem_slot = o; o += 16;
   o = (o + 15u) & ~15u;   // the bias rows are read with 128-bit shared loads
   L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
+  L.scale = o; o += 16 * 4;
   L.readout = o; o += kNodeMaxClasses * kMaxN * 4;            // classification weights [C][H]
   L.logits = o; o += kTsParts * kTileM * kNodeMaxClasses * 4; // partial logits [part][row][C]
   L.total = o;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     const int g = t / kMaxN, n = t - g * kMaxN;
     s_bias[t] = (n < a.g[g].N && a.g[g].bias >= 0) ? Wp[a.g[g].bias + n] : 0.f;
   }
+  if (threadIdx.x < a.n_gemms) reinterpret_cast<float*>(smem + L.scale)[threadIdx.x] = a.wtc[a.g[threadIdx.x].unscale];
   float* s_readout = reinterpret_cast<float*>(smem + L.readout);
   float* s_logits = reinterpret_cast<float*>(smem + L.logits);
   if (a.do_readout)
@@ -332,6 +335,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         const uint32_t d_col = dbuf * kMaxN;
         const int nchunks = G.N / 64, nh = G.N / kTsNSplit;
         const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
+        const float unscale = lds32(s_base + L.scale + (uint32_t)g * 4u);   // accumulator = 2^s x product
+        const uint64_t unscale2 = pack2(unscale, unscale);
         const bool becomes_a = (G.kind == kNodeChain || G.kind == kNodeChainAddU ||
                                 (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
         int waited = -1;
@@ -350,8 +355,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 #pragma unroll
             for (int j = 0; j < kTsCols / 4; ++j) {
               const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-              silu2(add2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
-              silu2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
+              silu2(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
+              silu2(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
             }
           } else if (G.kind == kNodeChainAddU) {
             float u[kTsCols];
@@ -363,15 +368,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             }
 #pragma unroll
             for (int j = 0; j < kTsCols / 2; ++j)
-              silu2(add2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), pack2(u[2 * j], u[2 * j + 1])), v[2 * j], v[2 * j + 1]);
+              silu2(fma2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), unscale2, pack2(u[2 * j], u[2 * j + 1])), v[2 * j], v[2 * j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < kTsCols / 4; ++j) {
               const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), unscale, b.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), unscale, b.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), unscale, b.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), unscale, b.w);
             }
             if (G.kind == kNodeChainLast) {
               if (valid) {

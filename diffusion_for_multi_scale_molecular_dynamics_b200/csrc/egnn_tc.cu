@@ -43,12 +43,13 @@ struct EdgeTcArgs {
 };
 
 struct EdgeSmem {
-  uint32_t bias, wr, wlast, dot, total;
+  uint32_t bias, scale, wr, wlast, dot, total;
 };
 __host__ __device__ inline EdgeSmem edge_smem(int n_gemms) {
   EdgeSmem L;
   uint32_t o = pipe_smem().end;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
+  L.scale = o; o += 16 * 4;   // 2^-s of each GEMM's weight image (1 in the TF32 mode)
   L.wr = o; o += kMaxN * 4;
   L.wlast = o; o += kMaxN * 4;
   L.dot = o; o += kTileM * 4;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_tc_kernel(const EdgeTcA
   const Program& p = a.prog;
   const EdgeSmem L = edge_smem(p.n_gemms);
   float* s_bias = reinterpret_cast<float*>(smem + L.bias);
+  float* s_scale = reinterpret_cast<float*>(smem + L.scale);
   float* s_wr = reinterpret_cast<float*>(smem + L.wr);
   float* s_wlast = reinterpret_cast<float*>(smem + L.wlast);
   float* s_dot = reinterpret_cast<float*>(smem + L.dot);
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_tc_kernel(const EdgeTcA
     s_wr[t] = (t < M) ? p.packed[a.msg_wr + t] : 0.f;
     s_wlast[t] = (t < p.gN[p.n_gemms - 1]) ? p.packed[a.coord_last_w + t] : 0.f;
   }
+  if (threadIdx.x < p.n_gemms)
+    s_scale[threadIdx.x] = (PREC == kF16x3) ? p.wtc[p.gW[threadIdx.x] + weight_unscale_offset(p.gK[threadIdx.x], p.gN[threadIdx.x])] : 1.0f;
   Pipe<PREC> pipe;
   pipe.setup(smem);
   const TileSchedule sched = make_schedule(n_tiles);
@@ -154,12 +158,13 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_tc_kernel(const EdgeTcA
         const uint32_t acc_col = pipe.wait_accumulator();
         const int nchunks = p.gN[g] / kChunk;
         const float* bias = s_bias + g * kMaxN;
+        const float unscale = s_scale[g];
         for (int c = 0; c < nchunks; ++c) {
           const int col0 = c * kChunk + hh * kVals;
           float v[kVals];
           tmem_ld<kVals>(lane_taddr + acc_col + col0, v);
 #pragma unroll
-          for (int j = 0; j < kVals; ++j) v[j] = silu_fast(v[j] + bias[col0 + j]);
+          for (int j = 0; j < kVals; ++j) v[j] = silu_fast(fmaf(v[j], unscale, bias[col0 + j]));
           if (is_message) {  // agg[src] += m  (models/egnn.py:178-181)
 #pragma unroll
             for (int j = 0; j < kVals; ++j) {
@@ -201,11 +206,32 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_tc_kernel(const EdgeTcA
 
 #include "egnn_edge_ts.cuh"
 
-// ---- weight image (tc_common.cuh): TF32 parts [w_1 | w_2] per 32-K chunk, then fp16 parts [w_1 | w_2] per 64-K chunk
+// ---- weight image (tc_common.cuh): TF32 parts [w_1 | w_2] per 32-K chunk, then fp16 parts [w_1 | w_2] of 2^s w per
+// 64-K chunk, then the trailer [max |w|, 2^-s]
+__global__ void tc_absmax_kernel(const float* __restrict__ wt, int total, float* __restrict__ slot) {
+  float m = 0.f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const float w = fabsf(wt[t]);
+    if (w <= CUDART_MAX_NORMAL_F) m = fmaxf(m, w);   // NaN / inf weights do not set the scale
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned*>(slot), __float_as_uint(m));   // m >= 0: bit order = value order
+}
+// power of two that brings the largest weight magnitude into [2^14, 2^15) (1 for an all-zero matrix)
+__device__ __forceinline__ int f16_weight_exponent(float absmax) {
+  if (!(absmax > 0.f)) return 0;
+  int e;
+  frexpf(absmax, &e);   // absmax = m 2^e, m in [0.5, 1)
+  const int s = 15 - e;
+  return s < -100 ? -100 : (s > 100 ? 100 : s);
+}
 __global__ void tc_pack_kernel(const float* __restrict__ wt /* [K][N] */, int K, int N, float* __restrict__ dst) {
   const int total = K * N;
   __half* dst16 = reinterpret_cast<__half*>(dst + f16_image_offset(K, N));
   const int64_t part = (int64_t)N * 32;  // floats per part (N rows of 128 bytes)
+  const int s = f16_weight_exponent(dst[weight_absmax_offset(K, N)]);
+  const float scale = ldexpf(1.0f, s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) dst[weight_unscale_offset(K, N)] = ldexpf(1.0f, -s);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int n = t / K, k = t - n * K;
     const float w = wt[(int64_t)k * N + n];
@@ -217,9 +243,10 @@ __global__ void tc_pack_kernel(const float* __restrict__ wt /* [K][N] */, int K,
       dst[((int64_t)c * 2 + 0) * part + inner] = w1;
       dst[((int64_t)c * 2 + 1) * part + inner] = w - w1;
     }
-    if ((K & 63) == 0) {  // fp16 image: 2-byte elements, 64 per row, 8 per 16-byte unit
-      const __half h1 = __float2half_rn(w);
-      const __half h2 = __float2half_rn(w - __half2float(h1));
+    if ((K & 63) == 0) {  // fp16 image of 2^s w: 2-byte elements, 64 per row, 8 per 16-byte unit
+      const float ws = w * scale;   // exact (power of two, no overflow: |ws| < 2^15)
+      const __half h1 = __float2half_rn(ws);
+      const __half h2 = __float2half_rn(ws - __half2float(h1));
       const int c = k >> 6, kk = k & 63;
       const int64_t inner = (int64_t)(n >> 3) * 512 + sw * 64 + (((kk >> 3) ^ sw) << 3) + (kk & 7);
       dst16[((int64_t)c * 2 + 0) * part * 2 + inner] = h1;
@@ -258,6 +285,9 @@ EdgePlan make_edge_plan(const b200md_egnn_config& cfg, const EgnnLayerOffsets& L
 
 namespace tc {
 int pack_weight_image(const float* wt, int K, int N, float* dst, cudaStream_t st) {
+  // the trailer slot is zero here: b200md_egnn_pack_weights clears the whole image first
+  { ProfileScope ps__(B200MD_KERNEL_OTHER, st); tc_absmax_kernel<<<64, 256, 0, st>>>(wt, K * N, dst + weight_absmax_offset(K, N)); }
+  B200MD_CHECK_LAUNCH();
   { ProfileScope ps__(B200MD_KERNEL_OTHER, st); tc_pack_kernel<<<128, 256, 0, st>>>(wt, K, N, dst); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
@@ -282,14 +312,15 @@ namespace b200md {
 #endif
 
 int tc_sm_count() {
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
+  static int n_sm[PerDeviceOnce::kMaxDevices] = {};   // per device ordinal
+  const int dev = current_device();
+  if (dev < 0 || dev >= PerDeviceOnce::kMaxDevices) return 148;
+  if (n_sm[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n_sm[dev] = n > 0 ? n : 148;
   }
-  return n_sm;
+  return n_sm[dev];
 }
 
 // `precision`: the K chunk (and so the width granularity) is 32 for kTf32x3 and 64 for kF16x3
@@ -303,8 +334,8 @@ bool tc_edge_supported(const b200md_egnn_config& cfg, int precision) {
 }
 
 int64_t tc_edge_packed_floats(const b200md_egnn_config& cfg) {
-  const int64_t M = cfg.message_hidden, Cx = cfg.coord_hidden;
-  return 3 * (cfg.message_n_hidden * M * M + M * Cx + cfg.coord_n_hidden * Cx * Cx);
+  const int M = cfg.message_hidden, Cx = cfg.coord_hidden;
+  return cfg.message_n_hidden * weight_image_floats(M, M) + weight_image_floats(M, Cx) + cfg.coord_n_hidden * weight_image_floats(Cx, Cx);
 }
 
 int tc_edge_pack_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, int layer, float* packed, cudaStream_t st) {
@@ -336,15 +367,15 @@ int tc_launch_edge_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, i
   a.status = status;
   const bool ts = (precision == kF16x3Ts);
   const size_t smem = (ts ? ts_smem(plan.n).total : edge_smem(plan.n).total) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     cudaError_t e0 = cudaFuncSetAttribute(egnn_edge_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e0 != cudaSuccess) return set_cuda_error(e0);
     cudaError_t e1 = cudaFuncSetAttribute(egnn_edge_tc_kernel<kTf32x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaError_t e2 = cudaFuncSetAttribute(egnn_edge_tc_kernel<kF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e1 != cudaSuccess) return set_cuda_error(e1);
     if (e2 != cudaSuccess) return set_cuda_error(e2);
-    attr_set = true;
+    attr_set.done();
   }
   if (ts) {
     ProfileScope ps__(B200MD_KERNEL_EDGE, st);

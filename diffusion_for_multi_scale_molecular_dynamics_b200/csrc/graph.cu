@@ -309,6 +309,10 @@ int launch_egnn_graph(const float* x_rel, const float* lattice, float clip_min, 
   const float rc2 = rc * rc;  // radial_cutoff**2 on a float32 tensor (neighbors.py:103,172)
   int threads = N >= 256 ? 256 : (N >= 64 ? 128 : 64);
   size_t smem = (size_t)(3 * N + 81) * sizeof(float);
+  if (smem > 48 * 1024) {   // N > 4069: above the default dynamic shared-memory limit
+    cudaError_t e = cudaFuncSetAttribute(egnn_graph_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
   { ProfileScope ps__(B200MD_KERNEL_GRAPH, st); egnn_graph_count_kernel<<<(unsigned)B, threads, smem, st>>>(x_rel, lattice, clip_min, rc, rc2, N, W,
                                                               fully_connected, bitmask, deg, struct_total, status); }
   B200MD_CHECK_LAUNCH();

@@ -12,9 +12,18 @@
 //                  8 bytes per weight and chunk streamed from L2;
 //   mode kF16x3  : x_1 = fp16(x), x_2 = fp16(x - x_1): the same 11-bit significands as TF32 in 2-byte containers,
 //                  kind::f16, K chunk = 64 elements, 4 bytes per weight -- half the L2 -> SM traffic (the measured
-//                  bottleneck of the TF32 version) and half the tensor-pipe time.  fp16 has a 5-bit exponent: operands
-//                  below 6e-5 lose relative (not absolute) precision, and activations above 65504 saturate; the
-//                  epilogue raises B200MD_STATUS_TC_RANGE in the device status word when that happens.
+//                  bottleneck of the TF32 version) and half the tensor-pipe time.  fp16 has a 5-bit exponent, so the
+//                  exponent is managed explicitly:
+//                    * weights: every matrix is multiplied by a power of two 2^s chosen at pack time so that its
+//                      largest magnitude lands in [2^14, 2^15) (tc_pack_kernel); w_2 = fp16(2^s w - w_1) is then a
+//                      NORMAL fp16 number for every element within 2^-17 of the largest one, whatever the scale of a
+//                      trained checkpoint's weights (1e-3 or 1e+2 alike).  The accumulator holds 2^s times the
+//                      product; the epilogue undoes it exactly with one FMA, v = acc * 2^-s + bias (the factor is
+//                      stored next to the image, see weight_unscale_offset).
+//                    * activations: stored unscaled.  x_2 is subnormal for |x| < 0.25 (absolute error 2^-25 ~ 3e-8 per
+//                      element, harmless unless a whole layer's activations sit below ~1e-2), and an activation above
+//                      65504 becomes inf: the epilogue raises B200MD_STATUS_TC_RANGE in the device status word and the
+//                      host re-runs the call with the 3xTF32 kernels (fp32 exponent range).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -50,9 +59,13 @@ struct Mode {
 constexpr int kCluster = 1;
 // Global weight image of one Linear(K -> N), every part already in the 128B-swizzled K-major shared-memory layout
 // (N rows of 128 bytes): first the TF32 image -- per 32-element K chunk [w_1 (fp32 bits)] [w_2 (fp32 bits)], 2 K N
-// floats -- then the fp16 image -- per 64-element K chunk [w_1 (fp16)] [w_2 (fp16)], K N floats.
-__host__ __device__ inline int64_t weight_image_floats(int K, int N) { return (int64_t)3 * K * N; }
+// floats -- then the fp16 image of 2^s w -- per 64-element K chunk [w_1 (fp16)] [w_2 (fp16)], K N floats -- then a
+// 256-byte trailer: [max |w|] [2^-s] (the TF32 image is not scaled: TF32 has the fp32 exponent).
+constexpr int kWeightTrailerFloats = 64;
+__host__ __device__ inline int64_t weight_image_floats(int K, int N) { return (int64_t)3 * K * N + kWeightTrailerFloats; }
 __host__ __device__ inline int64_t f16_image_offset(int K, int N) { return (int64_t)2 * K * N; }
+__host__ __device__ inline int64_t weight_absmax_offset(int K, int N) { return (int64_t)3 * K * N; }
+__host__ __device__ inline int64_t weight_unscale_offset(int K, int N) { return (int64_t)3 * K * N + 1; }
 
 struct Program {
   const float* wtc;      // base of the weight images

@@ -118,6 +118,7 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
         self._last_time_step = False
         self._corrector_phase = 0
         self._seed_is_set = False
+        self._standalone_calls = 0
 
     # ---- device-side bookkeeping ---------------------------------------------------------------------------
     def _tables_on(self, device: torch.device):
@@ -148,6 +149,17 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
             self._active_seed = int(self.seed)
         self.trajectory_initializer.seed = self._active_seed
         self.trajectory_initializer.sample_offset = int(self.sample_offset)
+
+    def _begin_standalone_step(self) -> None:
+        """``predictor_step`` / ``corrector_step`` called outside ``sample()``: every call draws fresh noise, as in
+        the reference (whose draws advance the global generator).  The draws are keyed by (seed, step index), so the
+        seed itself has to change from call to call: taken from torch's global CPU generator (``torch.manual_seed``
+        controls it) or, when ``self.seed`` is set, derived from it and a call counter."""
+        self._standalone_calls += 1
+        if self.seed is None:
+            self._active_seed = int(torch.randint(0, 2**62, (1,)).item())
+        else:
+            self._active_seed = (int(self.seed) + 0x9E3779B97F4A7C15 * self._standalone_calls) % 2**64
 
     def _phase_id(self, index_i: int, corrector_phase: int) -> int:
         """Step key of the counter-based draws: i * (1 + n_corr) + phase (0 = predictor, k+1 = k-th corrector)."""
@@ -321,6 +333,8 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
             "The predictor step can only be invoked for index_i between 1 and the total number of discretization steps."
         device = composition_i.X.device
         self._device = device
+        if not self._in_trajectory:
+            self._begin_standalone_step()
         number_of_samples, number_of_atoms, d = composition_i.X.shape
         idx = index_i - 1
         self._step_id = self._phase_id(idx, 0)
@@ -379,6 +393,8 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
             "the total number of discretization steps minus 1.")
         device = composition_i.X.device
         self._device = device
+        if not self._in_trajectory:
+            self._begin_standalone_step()
         number_of_samples, number_of_atoms, d = composition_i.X.shape
         phase = self._corrector_phase
         self._step_id = self._phase_id(index_i, 1 + phase)
@@ -460,18 +476,32 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
         fused = self._run_fused(start, starting_step_index, ending_step_index)
         if fused is not None:
             return fused
-        composition_ip1 = start
-        forces = torch.zeros_like(composition_ip1.X)
-        composition_i = composition_ip1
-        for i in range(starting_step_index - 1, max(ending_step_index, 0) - 1, -1):
-            composition_i = self.predictor_step(composition_ip1, i + 1, forces)
-            for k in range(self.number_of_corrector_steps):
-                self._corrector_phase = k
-                composition_i = self.corrector_step(composition_i, i, forces)
-            self._corrector_phase = 0
-            composition_ip1 = composition_i
+        for attempt in range(2):
+            composition_ip1 = start
+            forces = torch.zeros_like(composition_ip1.X)
+            composition_i = composition_ip1
+            for i in range(starting_step_index - 1, max(ending_step_index, 0) - 1, -1):
+                composition_i = self.predictor_step(composition_ip1, i + 1, forces)
+                for k in range(self.number_of_corrector_steps):
+                    self._corrector_phase = k
+                    composition_i = self.corrector_step(composition_i, i, forces)
+                self._corrector_phase = 0
+                composition_ip1 = composition_i
+            # an fp16 overflow inside the network (IMPL_AUTO): the trajectory is run again from `start` with the
+            # wider-range kernels; the counter-based draws make it the trajectory those kernels give from the outset
+            if attempt == 0 and self._network_widened_its_range():
+                continue
+            break
         self._raise_on_status()
         return composition_i
+
+    def _network_widened_its_range(self) -> bool:
+        widen = getattr(self.axl_network, "widen_range_after_overflow", None)
+        if widen is None or not widen():
+            return False
+        if self._status is not None:
+            self._status.zero_()  # bits raised downstream of the overflow (NaN logits, MASK left): the re-run decides
+        return True
 
     @classmethod
     def _fused_classes(cls):
@@ -506,8 +536,6 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
         self._device = device
         lib = _cabi.lib()
         number_of_samples, number_of_atoms, _ = start.X.shape
-        x = _cabi.as_f32(start.X).clone()
-        a = _cabi.as_i64(start.A).clone()
         lattice = _cabi.as_f32(start.L)
         cfg = network._config()
         packed = network.packed_weights(device)
@@ -532,11 +560,21 @@ class LangevinGenerator(PredictorCorrectorAXLGenerator):
             x0_known=x0_known.data_ptr() if x0_known is not None else None,
             a0_known=a0_known.data_ptr() if a0_known is not None else None,
             constrained_indices=c_indices.data_ptr() if c_indices is not None else None)
-        status = self._status_on(device)
-        _cabi.check(lib.b200md_pc_sample(
-            ctypes.byref(cfg), _cabi.ptr(packed), ctypes.byref(schedule), _cabi.ptr(a), _cabi.ptr(x), _cabi.ptr(lattice),
-            number_of_samples, number_of_atoms, self._active_seed, int(self.sample_offset), _cabi.ptr(workspace),
-            workspace.numel(), capacity, _cabi.ptr(status), int(network.kernel_impl), _cabi.stream_ptr(device)))
+        # b200md_pc_sample and the network's own forward share ONE status word (the network's), so that an fp16
+        # overflow is seen by widen_range_after_overflow() whichever path raised it
+        status = network.device_status(device)
+        for attempt in range(2):
+            x = _cabi.as_f32(start.X).clone()
+            a = _cabi.as_i64(start.A).clone()
+            _cabi.check(lib.b200md_pc_sample(
+                ctypes.byref(cfg), _cabi.ptr(packed), ctypes.byref(schedule), _cabi.ptr(a), _cabi.ptr(x),
+                _cabi.ptr(lattice), number_of_samples, number_of_atoms, self._active_seed, int(self.sample_offset),
+                _cabi.ptr(workspace), workspace.numel(), capacity, _cabi.ptr(status), network.effective_kernel_impl(),
+                _cabi.stream_ptr(device)))
+            # IMPL_AUTO and an activation beyond fp16: same trajectory (same counter-based noise) on the 3xTF32 kernels
+            if attempt == 0 and self._network_widened_its_range():
+                continue
+            break
         self._raise_on_status()
         return AXL(A=a, X=x, L=start.L)
 

@@ -92,7 +92,7 @@ class FullRandomTrajectoryInitializer(TrajectoryInitializer):
         else:
             lattice = torch.empty(number_of_samples, self.num_lattice_parameters, dtype=torch.float32, device=device)
             _cabi.check(lib.b200md_draw_normal(_cabi.ptr(lattice), number_of_samples, 1, self.num_lattice_parameters,
-                                               self.seed, 0, _cabi.DRAW_LATTICE_NORMAL, self.sample_offset,
+                                               self.seed, 0, _cabi.DRAW_INIT_LATTICE, self.sample_offset,
                                                _cabi.stream_ptr(device)))
         return AXL(A=atom_types, X=x, L=lattice)
 

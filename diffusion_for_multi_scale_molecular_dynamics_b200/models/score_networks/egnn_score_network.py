@@ -90,6 +90,9 @@ class EGNNScoreNetwork(ScoreNetwork):
         )
         # ---- sm_100a state (not part of the state_dict) ----
         self.kernel_impl = _cabi.IMPL_AUTO  # IMPL_FFMA / IMPL_TCGEN05 can be forced for A/B checks
+        # Set (and kept) once an activation of THIS network left the fp16 range of the 3xFP16 kernels under IMPL_AUTO:
+        # from then on AUTO means the 3xTF32 kernels, which have the fp32 exponent range.
+        self._auto_fallback_impl: Optional[int] = None
         self.edge_capacity: Optional[int] = None  # None -> b200md_egnn_default_edge_capacity
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
@@ -102,10 +105,37 @@ class EGNNScoreNetwork(ScoreNetwork):
         """Total number of directed edges of the graph used by the last ``forward`` (one host sync)."""
         return 0 if self._n_edges is None else int(self._n_edges.item())
 
+    def effective_kernel_impl(self) -> int:
+        """``kernel_impl``, or the wider-range implementation IMPL_AUTO has fallen back to for this network."""
+        if self.kernel_impl == _cabi.IMPL_AUTO and self._auto_fallback_impl is not None:
+            return self._auto_fallback_impl
+        return int(self.kernel_impl)
+
+    def widen_range_after_overflow(self, word: Optional[int] = None) -> bool:
+        """IMPL_AUTO only: if the status word says an activation overflowed fp16 (STATUS_TC_RANGE), clear the bit,
+        switch this network to the 3xTF32 kernels for good and tell the caller to evaluate again.  A forced
+        ``kernel_impl`` keeps the bit, which is then raised as an AssertionError."""
+        if self.kernel_impl != _cabi.IMPL_AUTO or self._auto_fallback_impl is not None or self._status is None:
+            return False
+        cfg = self._config()
+        lib = _cabi.lib()
+        if lib.b200md_egnn_resolve_impl(ctypes.byref(cfg), _cabi.IMPL_AUTO) not in (_cabi.IMPL_TCGEN05_F16X3,
+                                                                                   _cabi.IMPL_TCGEN05_F16X3_TS):
+            return False
+        if lib.b200md_egnn_resolve_impl(ctypes.byref(cfg), _cabi.IMPL_TCGEN05) != _cabi.IMPL_TCGEN05:
+            return False
+        if word is None:
+            word = _cabi.status_word(self._status)
+        if not word & _cabi.STATUS_TC_RANGE:
+            return False
+        self._status.zero_()  # inf / NaN downstream of the overflow may have raised other bits; the re-run raises the real ones
+        self._auto_fallback_impl = _cabi.IMPL_TCGEN05
+        return True
+
     def last_edge_kernel_name(self) -> str:
         """Which edge-MLP implementation ``kernel_impl`` resolves to for this configuration."""
         cfg = self._config()
-        resolved = _cabi.lib().b200md_egnn_resolve_impl(ctypes.byref(cfg), int(self.kernel_impl))
+        resolved = _cabi.lib().b200md_egnn_resolve_impl(ctypes.byref(cfg), self.effective_kernel_impl())
         return {_cabi.IMPL_FFMA: "egnn_edge_kernel (fp32 FFMA tiles)",
                 _cabi.IMPL_TCGEN05: "egnn_edge_tc_kernel (tcgen05 3xTF32, fp32 accumulate in TMEM)",
                 _cabi.IMPL_TCGEN05_F16X3: "egnn_edge_tc_kernel (tcgen05 3xFP16, fp32 accumulate in TMEM)",
@@ -252,6 +282,5 @@ class EGNNScoreNetwork(ScoreNetwork):
             ctypes.byref(cfg), _cabi.ptr(packed), _cabi.ptr(a), _cabi.ptr(x), _cabi.ptr(lattice), _cabi.ptr(sigma),
             batch_size, number_of_atoms, int(self._fuse_mask_logit), _cabi.ptr(logits), _cabi.ptr(scores),
             _cabi.ptr(workspace), workspace.numel(), capacity, _cabi.ptr(self._n_edges), _cabi.ptr(status),
-            int(self.kernel_impl),
-            _cabi.stream_ptr(device)))
+            self.effective_kernel_impl(), _cabi.stream_ptr(device)))
         return AXL(A=logits, X=scores, L=torch.zeros_like(composition.L))

@@ -116,10 +116,20 @@ class ScoreNetwork(torch.nn.Module):
             # The reference's conditional branch multiplies AXL namedtuples by floats and cannot run (:213-219).
             raise NotImplementedError("conditional score evaluation is not available on the sampling path")
         output = self._forward_unchecked(batch, conditional=False)
-        self._impose_non_mask_atomic_type_prediction(output)
         if not self.defer_status_check:
-            self.raise_on_device_status()
+            word = _cabi.status_word(self._status)  # the one host synchronisation of this call
+            if word and self.widen_range_after_overflow(word):
+                output = self._forward_unchecked(batch, conditional=False)  # once more, with the wider-range kernels
+                word = _cabi.status_word(self._status)
+            _cabi.raise_for_word(word, self._status, AssertionError)
+        self._impose_non_mask_atomic_type_prediction(output)
         return output
+
+    def widen_range_after_overflow(self, word: Optional[int] = None) -> bool:
+        """True when the last evaluation overflowed a reduced-range kernel AND the network has now switched to a
+        wider-range implementation, i.e. the caller should evaluate again (see EGNNScoreNetwork).  ``word`` is the
+        status word if the caller has read it already."""
+        return False
 
     def _forward_unchecked(self, batch: Dict[AnyStr, torch.Tensor], conditional: bool = False) -> AXL:
         raise NotImplementedError

@@ -83,6 +83,7 @@ int b200md_profile_collect(double* ms_by_class_host, int64_t* launches_by_class_
 #define B200MD_DRAW_REPAINT_UNIFORM 6u
 #define B200MD_DRAW_REPAINT_INIT 7u
 #define B200MD_DRAW_LATTICE_NORMAL_2 8u /* the corrector's second lattice draw (langevin_generator.py:771-777) */
+#define B200MD_DRAW_INIT_LATTICE 9u     /* the starting lattice of a free-lattice trajectory (trajectory_initializer.py:114-121) */
 
 int b200md_draw_normal(float* out, int64_t n_samples, int32_t units_per_sample, int32_t unit_size,
                        uint64_t seed, uint32_t step_id, uint32_t draw_id, uint64_t sample_offset,

@@ -9,8 +9,7 @@ from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.egn
 from diffusion_for_multi_scale_molecular_dynamics_b200.utils.basis_transformations import \
     map_relative_coordinates_to_unit_cell
 from diffusion_for_multi_scale_molecular_dynamics_b200.utils.structure_utils import compute_distances_in_batch
-from oracle import pc_oracle as oracle
-from tests.test_gpu_parity import PRODUCTION, SCORE_CANCELLATION_FLOOR, assert_rel, network_batch
+from tests.test_gpu_parity import PRODUCTION, assert_anchored, network_batch, oracle_forward_both
 
 pytestmark = pytest.mark.gpu
 
@@ -26,8 +25,7 @@ def forward_both(cuda_device, hp, a, x, lattice, sigma, impl=_cabi.IMPL_AUTO, se
     net = net.to(cuda_device)
     net.kernel_impl = impl
     out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
-    logits, score = oracle.egnn_score_forward(sd, dict(FULL, **hp), a, x, lattice, sigma)
-    return net, out, logits, score
+    return net, out, oracle_forward_both(sd, dict(FULL, **hp), a, x, lattice, sigma)
 
 
 @pytest.mark.parametrize("impl", [_cabi.IMPL_FFMA, _cabi.IMPL_TCGEN05_F16X3_TS], ids=["ffma", "f16x3ts"])
@@ -46,9 +44,9 @@ def test_egnn_degenerate_graphs(cuda_device, B, N, edges, impl):
     lattice = torch.zeros(B, 6)
     lattice[:, :3] = 9.0
     sigma = torch.rand(B, 1) * 0.3 + 0.01
-    net, out, logits, score = forward_both(cuda_device, hp, a, x, lattice, sigma, impl)
-    assert_rel(out.A, logits, 1e-5, "logits")
-    assert_rel(out.X, score, 1e-5, "score", floor=SCORE_CANCELLATION_FLOOR)
+    net, out, (logits32, score32, logits64, score64) = forward_both(cuda_device, hp, a, x, lattice, sigma, impl)
+    assert_anchored(out.A, logits32, logits64, "logits")
+    assert_anchored(out.X, score32, score64, "score")
     if (B, N) == (64, 2):
         assert net.last_number_of_edges() == 128
     if N == 1:
@@ -86,13 +84,13 @@ def test_score_network_invariances_at_the_largest_supercell(cuda_device):
     shifted = torch.remainder(x + torch.tensor([0.31, 0.77, 0.05]), 1.0)
     moved = net(network_batch(a, shifted, lattice, sigma, cuda_device), conditional=False)
     scale = base.X.abs().max()
-    # S = z . Gamma . zhat is a difference of unit-size fp32 numbers: 2^-22 is the floor of any evaluation order
-    assert (moved.X - base.X).abs().max() <= 2e-4 * scale + SCORE_CANCELLATION_FLOOR
+    # two evaluations of the same fp32 kernel on differently rounded inputs: the translation changes every rounding
+    assert (moved.X - base.X).abs().max() <= 2.5e-4 * scale
     finite = torch.isfinite(base.A)
     assert (moved.A[finite] - base.A[finite]).abs().max() <= 2e-4 * base.A[finite].abs().max()
     perm = torch.randperm(N)
     permuted = net(network_batch(a[:, perm], x[:, perm], lattice, sigma, cuda_device), conditional=False)
-    assert (permuted.X - base.X[:, perm.to(cuda_device)]).abs().max() <= 2e-5 * scale + SCORE_CANCELLATION_FLOOR
+    assert (permuted.X - base.X[:, perm.to(cuda_device)]).abs().max() <= 6e-5 * scale  # two summation orders of one fp32 kernel, each ~1.5e-5 from the exact value
     assert (permuted.A[finite[:, perm.to(cuda_device)]] - base.A[:, perm.to(cuda_device)][finite[:, perm.to(cuda_device)]]
             ).abs().max() <= 2e-5 * base.A[finite].abs().max()
 

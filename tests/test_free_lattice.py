@@ -98,3 +98,50 @@ def test_free_lattice_native_noise(cuda_device):
     assert torch.equal(part.A, full.A[3:5])
     torch.testing.assert_close(part.L, full.L[3:5], rtol=1e-5, atol=1e-5)
     assert not torch.allclose(full.L[0], full.L[1])
+
+
+def test_every_draw_of_a_trajectory_has_its_own_counter_key(cuda_device):
+    """The counter-based generator returns the same numbers for the same (seed, sample, step id, draw id): no two draws of
+    a trajectory may share (step id, draw id).  In particular the starting lattice L_T must not reuse the key of the last
+    predictor step's lattice noise (step id 0, DRAW_LATTICE_NORMAL)."""
+    from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+    g = load_golden("free_lattice")
+    gen, T = build(g, cuda_device)
+    gen.seed = 11
+    keys = [(0, _cabi.DRAW_INIT_UNIFORM), (0, _cabi.DRAW_INIT_LATTICE)]   # FullRandomTrajectoryInitializer.initialize
+    original = gen._draw
+
+    def recording_draw(kind, number_of_samples, units, unit_size, draw_id):
+        keys.append((gen._step_id, draw_id))
+        return original(kind, number_of_samples, units, unit_size, draw_id)
+
+    with mock.patch.object(gen, "_draw", side_effect=recording_draw):
+        final = gen.sample(4, cuda_device)
+    assert len(keys) > 4 * T and len(set(keys)) == len(keys), sorted(k for k in keys if keys.count(k) > 1)
+    # and the starting lattice differs from the noise the last predictor step adds
+    start = gen.trajectory_initializer.initialize(4, cuda_device)
+    gen._device, gen._step_id = cuda_device, 0
+    last_noise = gen._draw_lattice_gaussian_sample(4)
+    assert not torch.equal(start.L, last_noise) and bool(torch.isfinite(final.L).all())
+
+
+def test_standalone_steps_draw_fresh_noise(cuda_device):
+    """corrector_step / predictor_step called outside sample() (a user-written Langevin loop): consecutive calls at the
+    same time index must not reuse their noise -- in the reference every call advances the global generator."""
+    g = load_golden("free_lattice")
+    gen, _ = build(g, cuda_device)
+    start = AXL(A=g["a0"].to(cuda_device), X=g["x0"].to(cuda_device), L=g["l"].to(cuda_device))
+    forces = torch.zeros_like(start.X)
+    for seed in (None, 5):
+        gen.seed = seed
+        torch.manual_seed(0)
+        first = gen.corrector_step(start, 2, forces)
+        second = gen.corrector_step(start, 2, forces)
+        assert not torch.equal(first.X, second.X) and not torch.equal(first.L, second.L)
+        p1, p2 = gen.predictor_step(start, 3, forces), gen.predictor_step(start, 3, forces)
+        assert not torch.equal(p1.X, p2.X)
+    gen.seed = None
+    torch.manual_seed(0)   # torch.manual_seed still controls reproducibility
+    again = gen.corrector_step(start, 2, forces)
+    torch.manual_seed(0)
+    assert torch.equal(gen.corrector_step(start, 2, forces).X, again.X)

@@ -2,8 +2,10 @@
 the C ABI of include/b200md.h), against the golden vectors of the unmodified reference and against the CPU oracle
 on seeded inputs.
 
-Tolerances (fp32): integer / index outputs are bit-exact; the EGNN score and logits are compared at 1e-5 relative to
-the largest reference magnitude of the tensor (``assert_rel``); one predictor-corrector step at 1e-5 on the torus.
+Tolerances (fp32): integer / index outputs are bit-exact; one predictor-corrector step at 1e-5 on the torus.  The EGNN
+score and logits are judged against an fp64 evaluation of the same network (``assert_anchored``): the kernel must be
+within 1e-5 (relative to the largest magnitude of the tensor) of the exact value, or at least as close to it as the
+fp32 reference itself is -- no absolute floor.
 """
 from unittest import mock
 
@@ -42,12 +44,6 @@ from tests.egnn_variants import EGNN_VARIANTS, hyper_parameters
 pytestmark = pytest.mark.gpu
 
 
-# The sigma-normalised score is S = z . Gamma . zhat with |z| = 1 and zhat = z + O(1e-2): a difference of unit-size
-# fp32 numbers.  Two ulps of those operands (2^-22) is therefore the floor of ANY fp32 evaluation order, whatever
-# the size of S; it is added to the 1e-5 relative bound for the projected score only.
-SCORE_CANCELLATION_FLOOR = 2.0 ** -22
-
-
 def assert_rel(actual: torch.Tensor, expected: torch.Tensor, rel: float = 1e-5, what: str = "", floor: float = 0.0):
     """max |actual - expected| <= rel * max |expected| + floor (finite entries; non-finite entries must coincide)."""
     actual, expected = actual.detach().cpu(), expected.detach().cpu()
@@ -57,6 +53,50 @@ def assert_rel(actual: torch.Tensor, expected: torch.Tensor, rel: float = 1e-5, 
     scale = expected[finite].abs().max().item()
     err = (actual[finite] - expected[finite]).abs().max().item()
     assert err <= rel * scale + floor, f"{what}: max abs err {err:.3e} > {rel:g} x {scale:.3e} + {floor:.1e}"
+
+
+def assert_anchored(actual: torch.Tensor, ref32: torch.Tensor, ref64: torch.Tensor, what: str = "", rel: float = 1e-5):
+    """The parity criterion of the score network, anchored on the exact value instead of on one fp32 evaluation order:
+
+        max |actual - ref64|  <=  max( rel * max |ref64| ,  max |ref32 - ref64| )
+
+    ``ref32`` is the reference's fp32 result (golden file or fp32 oracle), ``ref64`` the fp64 oracle on the same
+    weights and inputs.  The score S = z . Gamma . zhat is a difference of unit-size fp32 numbers, so two fp32
+    evaluation orders differ by more than 1e-5 of max |S| (the reference's own CPU result is 1.8e-5 from the exact value
+    at production widths); what can be asked of the kernel is to be within the contract of the exact value or no
+    farther from it than the reference is.  Non-finite entries (the MASK logit) must coincide."""
+    actual, ref32, ref64 = actual.detach().cpu().double(), ref32.detach().cpu().double(), ref64.detach().cpu().double()
+    finite = torch.isfinite(ref64)
+    assert torch.equal(torch.isfinite(actual), finite), f"{what}: non-finite pattern differs"
+    assert torch.equal(actual[~finite], ref64[~finite]), f"{what}: non-finite values differ"
+    scale = ref64[finite].abs().max().item()
+    err = (actual[finite] - ref64[finite]).abs().max().item()
+    err_reference = (ref32[finite] - ref64[finite]).abs().max().item()
+    bound = max(rel * scale, err_reference)
+    assert err <= bound, (f"{what}: |kernel - fp64| = {err:.3e} ({err / scale:.2e} rel) > max({rel:g} x {scale:.3e}, "
+                          f"|fp32 reference - fp64| = {err_reference:.3e})")
+
+
+_FULL_HP = dict(residual=True, attention=False, normalize=False, tanh=False, coords_agg="mean", message_agg="mean")
+
+
+def oracle_edges(hp: dict, x: torch.Tensor, lattice: torch.Tensor):
+    """The edge list both precisions of the oracle share (the fp32 cutoff decisions are part of the contract)."""
+    if hp.get("edges", "fully_connected") == "fully_connected":
+        return oracle.fully_connected_edges(x.shape[1], x.shape[0])
+    rc = hp["radial_cutoff"]
+    lp = lattice.clip(min=2.2 * rc)
+    return oracle.edges_with_radial_cutoff(x, torch.diag_embed(lp[:, :3]), rc)
+
+
+def oracle_forward_both(sd: dict, hp: dict, a, x, lattice, sigma):
+    """(logits32, score32, logits64, score64) of the CPU oracle on one state dict, in fp32 and in fp64."""
+    hp = dict(_FULL_HP, **hp)
+    edges = oracle_edges(hp, x, lattice)
+    logits32, score32 = oracle.egnn_score_forward(sd, hp, a, x, lattice, sigma, edges=edges)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    logits64, score64 = oracle.egnn_score_forward(sd64, hp, a, x.double(), lattice.double(), sigma.double(), edges=edges)
+    return logits32, score32, logits64, score64
 
 
 def torus_distance(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -271,8 +311,11 @@ def test_egnn_forward_golden(cuda_device, variant):
     g = sub_dict(load_golden("egnn_forward"), variant)
     net = make_network(variant, sub_dict(g, "sd"), cuda_device)
     out = net(network_batch(g["a"], g["x"], g["l"], g["sigma"], cuda_device), conditional=False)
-    assert_rel(out.X, g["score"], 1e-5, f"{variant} score", floor=SCORE_CANCELLATION_FLOOR)
-    assert_rel(out.A, g["logits"], 1e-5, f"{variant} logits")
+    # the reference's own fp32 output (golden) and the fp64 oracle on the same state dict
+    _, _, logits64, score64 = oracle_forward_both(sub_dict(g, "sd"), hyper_parameters(variant), g["a"], g["x"], g["l"],
+                                                  g["sigma"])
+    assert_anchored(out.X, g["score"], score64, f"{variant} score")
+    assert_anchored(out.A, g["logits"], logits64, f"{variant} logits")
     assert torch.equal(out.L.cpu(), torch.zeros_like(g["l"]))
 
 
@@ -288,9 +331,17 @@ def test_egnn_state_dict_is_reference_compatible():
     assert torch.equal(own["projection_matrices"], reference["projection_matrices"])
 
 
-def run_against_oracle(cuda_device, hp, N, B, length, impl, seed=5):
+_ORACLE_CACHE = {}
+
+
+def run_against_oracle(cuda_device, hp, N, B, length, impl, seed=5, mutate=None, mutate_key=None):
+    """Random-init network (optionally edited by ``mutate(net)``) on random structures: kernel vs the CPU oracle in fp32
+    and fp64 (``assert_anchored``).  The oracle results are cached per case so that the implementations share them."""
     torch.manual_seed(seed)
     net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
+    if mutate is not None:
+        with torch.no_grad():
+            mutate(net)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.to(cuda_device)
     net.kernel_impl = impl
@@ -301,11 +352,18 @@ def run_against_oracle(cuda_device, hp, N, B, length, impl, seed=5):
     lattice[:, :3] = length
     sigma = torch.rand(B, 1) * 0.4 + 0.005
     out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
-    full = dict(residual=True, attention=False, normalize=False, tanh=False, coords_agg="mean", message_agg="mean")
-    full.update(hp)
-    logits, score = oracle.egnn_score_forward(sd, full, a, x, lattice, sigma)
-    assert_rel(out.X, score, 1e-5, "score", floor=SCORE_CANCELLATION_FLOOR)
-    assert_rel(out.A, logits, 1e-5, "logits")
+    key = (tuple(sorted(hp.items())), N, B, length, seed, mutate_key if mutate is not None else None)
+    if mutate is not None and mutate_key is None:
+        key = None
+    if key is None or key not in _ORACLE_CACHE:
+        result = oracle_forward_both(sd, hp, a, x, lattice, sigma)
+        if key is not None:
+            _ORACLE_CACHE[key] = result
+    else:
+        result = _ORACLE_CACHE[key]
+    logits32, score32, logits64, score64 = result
+    assert_anchored(out.X, score32, score64, "score")
+    assert_anchored(out.A, logits32, logits64, "logits")
     return net
 
 
@@ -370,16 +428,80 @@ def test_ts_edge_kernel_short_segments(cuda_device, N, B):
     assert "ts" in net.last_edge_kernel_name()
 
 
-@pytest.mark.parametrize("impl", [_cabi.IMPL_TCGEN05_F16X3, _cabi.IMPL_TCGEN05_F16X3_TS], ids=["f16x3", "f16x3ts"])
-def test_fp16_range_guard(cuda_device, impl):
-    """3xFP16 kernels flag activations beyond the fp16 range instead of silently saturating."""
+def _linears(mlp):
+    return [m for m in mlp if isinstance(m, torch.nn.Linear)]
+
+
+def _scale_all_weights(factor):
+    """Every hidden Linear of every MLP scaled by ``factor`` and the Linear behind it by 1 / factor: the weights of a
+    trained checkpoint at another scale, with activations that stay representable (x factor between the two)."""
+    def mutate(net):
+        for layer in net.egnn.graph_layers:
+            for mlp in (layer.message_mlp, layer.node_mlp, layer.coord_mlp):
+                linears = _linears(mlp)
+                for first, second in zip(linears[0:-1:2], linears[1::2]):
+                    first.weight.mul_(factor)
+                    first.bias.mul_(factor)
+                    second.weight.div_(factor)
+    return mutate
+
+
+def _one_layer_tiny(net):
+    """One Linear of each MLP kind at the 1e-3 scale (1e-3 x default init, i.e. |w| < 1e-4): without the per-matrix
+    power-of-two scaling of the fp16 image its lo parts are subnormal and carry ~3e-5 relative error per weight."""
+    layer = net.egnn.graph_layers[0]
+    _linears(layer.message_mlp)[1].weight.mul_(1e-3)
+    _linears(layer.coord_mlp)[1].weight.mul_(1e-3)
+    _linears(layer.node_mlp)[1].weight.mul_(1e-3)
+    _linears(net.egnn.graph_layers[1].message_mlp)[0].weight.mul_(1e-3)   # P / Q of the second layer
+
+
+def _large_activations(net):
+    """Biases that push a quarter of the hidden activations of the message, coordinate and node MLPs to 1e3 - 1e4
+    (inside the fp16 range, far from the O(1) values of a random-init network)."""
+    layer = net.egnn.graph_layers[0]
+    for mlp, value in ((layer.message_mlp, 3.0e3), (layer.coord_mlp, 8.0e3), (layer.node_mlp, 2.0e3)):
+        bias = _linears(mlp)[1].bias
+        bias[: bias.numel() // 4] = value
+    _linears(layer.coord_mlp)[-1].weight.mul_(1e-4)   # keeps the coordinate update (and the score) finite and O(1)
+
+
+WEIGHT_SCALE_CASES = {
+    "x1e-2": _scale_all_weights(1e-2), "x1e+2": _scale_all_weights(1e2), "one-layer-1e-3": _one_layer_tiny,
+    "activations-1e3-1e4": _large_activations,
+}
+
+
+@pytest.mark.parametrize("case", list(WEIGHT_SCALE_CASES))
+@pytest.mark.parametrize("impl", [_cabi.IMPL_AUTO] + TC_IMPLS, ids=["auto"] + TC_IDS)
+def test_weight_and_activation_scales_against_oracle(cuda_device, case, impl):
+    """Checkpoints whose weights are NOT at the default-init scale (models/egnn.py:78-134: the MLPs whose trained
+    scales are arbitrary).  The 3xFP16 kernels keep fp32 accuracy through the power-of-two scaling of every weight
+    matrix (tc_common.cuh); same criterion as every other forward test."""
+    hp = dict(num_atom_types=2, edges="radial_cutoff", radial_cutoff=3.1, message_hidden_dimensions_size=128,
+              coordinate_hidden_dimensions_size=128, node_hidden_dimensions_size=128, message_n_hidden_dimensions=2,
+              coordinate_n_hidden_dimensions=2, node_n_hidden_dimensions=2, n_layers=2)
+    net = run_against_oracle(cuda_device, hp, 40, 5, 7.0, impl, seed=13, mutate=WEIGHT_SCALE_CASES[case], mutate_key=case)
+    assert "tcgen05" in net.last_edge_kernel_name()
+    if impl == _cabi.IMPL_AUTO:
+        assert "3xFP16" in net.last_edge_kernel_name()   # no fallback was needed: everything stayed inside fp16
+
+
+def _overflowing_network(cuda_device):
     hp = dict(num_atom_types=1, edges="radial_cutoff", radial_cutoff=3.1, message_hidden_dimensions_size=64,
               coordinate_hidden_dimensions_size=64, node_hidden_dimensions_size=64, n_layers=1)
     torch.manual_seed(3)
     net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
     with torch.no_grad():
         net.egnn.graph_layers[0].message_mlp[2].bias.fill_(1.0e6)  # pushes the message activations to ~1e6
-    net = net.to(cuda_device)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return hp, sd, net.to(cuda_device)
+
+
+@pytest.mark.parametrize("impl", [_cabi.IMPL_TCGEN05_F16X3, _cabi.IMPL_TCGEN05_F16X3_TS], ids=["f16x3", "f16x3ts"])
+def test_fp16_range_guard(cuda_device, impl):
+    """A FORCED 3xFP16 implementation flags activations beyond the fp16 range instead of silently saturating."""
+    _, _, net = _overflowing_network(cuda_device)
     x = torch.rand(2, 24, 3)
     a = torch.zeros(2, 24, dtype=torch.long)
     lattice = torch.zeros(2, 6)
@@ -391,6 +513,53 @@ def test_fp16_range_guard(cuda_device, impl):
     net.kernel_impl = _cabi.IMPL_TCGEN05
     out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)  # 3xTF32 has the fp32 range
     assert bool(torch.isfinite(out.X).all())
+
+
+def test_auto_falls_back_to_tf32_on_fp16_overflow(cuda_device):
+    """IMPL_AUTO: the same overflow re-runs the evaluation with the 3xTF32 kernels (fp32 exponent range) instead of
+    raising, the result is the oracle's, and the network stays on 3xTF32 afterwards.  The fused trajectory does the
+    same: it is run again from its start, and -- the noise being counter-based -- equals the 3xTF32 trajectory."""
+    hp, sd, net = _overflowing_network(cuda_device)
+    torch.manual_seed(4)
+    x = torch.rand(2, 24, 3)
+    a = torch.zeros(2, 24, dtype=torch.long)
+    lattice = torch.zeros(2, 6)
+    lattice[:, :3] = 7.0
+    sigma = torch.full((2, 1), 0.1)
+    assert net.kernel_impl == _cabi.IMPL_AUTO and "3xFP16" in net.last_edge_kernel_name()
+    out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
+    assert "3xTF32" in net.last_edge_kernel_name()
+    logits32, score32, logits64, score64 = oracle_forward_both(sd, hp, a, x, lattice, sigma)
+    assert_anchored(out.X, score32, score64, "score after the fallback")
+    assert_anchored(out.A, logits32, logits64, "logits after the fallback")
+
+    def trajectory(impl):
+        _, _, fresh = _overflowing_network(cuda_device)
+        fresh.kernel_impl = impl
+        sampling = PredictorCorrectorSamplingParameters(number_of_samples=4, number_of_atoms=24, num_atom_types=1,
+                                                        use_fixed_lattice_parameters=True, cell_dimensions=[7.0] * 3)
+        generator = LangevinGenerator(NoiseParameters(total_time_steps=4), sampling, fresh)
+        generator.seed = 99
+        return fresh, generator.sample(4, cuda_device)
+
+    auto_net, auto = trajectory(_cabi.IMPL_AUTO)
+    assert auto_net._auto_fallback_impl == _cabi.IMPL_TCGEN05
+    _, tf32 = trajectory(_cabi.IMPL_TCGEN05)
+    assert torch.equal(auto.A, tf32.A)
+    assert torch.isfinite(auto.X).all() and torus_distance(auto.X, tf32.X).max() < 1e-4
+
+
+@pytest.mark.parametrize("num_atom_types,N,B,length", [(1, 64, 64, 10.86), (2, 512, 1, 21.72), (1, 512, 2, 21.72)],
+                         ids=["Si2x2x2-64-structures", "SiGe4x4x4-1-structure", "Si4x4x4-2-structures"])
+def test_production_kernels_many_tiles_against_oracle(cuda_device, num_atom_types, N, B, length):
+    """The production (IMPL_AUTO = tensor-memory) kernels against the oracle at sizes where every CTA of the persistent
+    edge kernel runs several tiles: 64 x Si 2x2x2 = ~800 edge tiles on 148 CTAs (5-6 tiles each: the next tile's first
+    activation written in place, ring wrap-around, the empty tail tile of a cluster) and the 512-atom supercells of
+    config 5 (~350 / ~700 tiles; 88 edges per atom, i.e. segments longer than a warp's 32 rows)."""
+    net = run_against_oracle(cuda_device, dict(num_atom_types=num_atom_types, **PRODUCTION), N, B, length, _cabi.IMPL_AUTO,
+                             seed=17)
+    assert "egnn_edge_ts_kernel" in net.last_edge_kernel_name()
+    assert net.last_number_of_edges() > 128 * 300
 
 
 def test_tcgen05_unsupported_configuration_is_refused(cuda_device):
