@@ -42,11 +42,10 @@ WORKLOADS = {
     "cfg1": ("Si 1x1x1 (8 atoms) EGNN, fully connected, PC Langevin", 8, 5.43, 1, dict(), 4096),
 }
 TOTAL_TIME_STEPS = 1000
-# dram__bytes_read.sum + dram__bytes_write.sum of one edge-kernel launch (ncu --set full at 4096 samples:
-# profiles/ncu_full_r01l.txt for egnn_edge_ts_kernel, ncu_full_r01f.txt for the shared-memory 3xFP16 kernel); the
-# algorithmic HBM bytes of a launch are the P / Q / agg rows: 3 x samples x atoms x 1 KB = 805 MB
-NCU_TRAFFIC_BYTES = {("cfg2", 4096, "auto"): 874701312 + 253051648, ("cfg2", 4096, "f16x3ts"): 874701312 + 253051648,
-                     ("cfg2", 4096, "f16x3"): 874239488 + 254038784}
+# roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum of one edge-kernel launch) cannot be measured from inside
+# this process; it is null on the line and the ncu --set full capture of the same command is committed under profiles/
+# (ncu_full_*.txt: 1.128 GB per launch at 4096 samples against 0.805 GB of algorithmic P / Q / agg rows).
+NCU_TRAFFIC_NOTE = "null: not measured in-run; see profiles/ncu_full_*.txt (ncu --set full of this command)"
 PRODUCTION = dict(n_layers=4, message_n_hidden_dimensions=4, message_hidden_dimensions_size=256,
                   node_n_hidden_dimensions=4, node_hidden_dimensions_size=256, coordinate_n_hidden_dimensions=4,
                   coordinate_hidden_dimensions_size=256)
@@ -89,6 +88,17 @@ def algorithmic_flops(hp: dict, n_atoms: int, edges_per_structure: float) -> dic
     per_forward = layers * (edges_per_structure * f_edge + n_atoms * f_node) + n_atoms * (2 * F0 * H + 2 * H * C)
     return dict(f_edge=f_edge, f_node=f_node, per_forward=per_forward,
                 edge_per_forward=layers * edges_per_structure * f_edge)
+
+
+def workload_config(workload: str, samples_per_gpu: int, world: int) -> dict:
+    """The `config` object of the JSON line: identical for the B200 arm and the reference arm on the same workload."""
+    description, atoms, _, _, _, _ = WORKLOADS[workload]
+    return {"workload": f"{workload}: {description}", "samples_per_gpu": samples_per_gpu, "atoms": atoms,
+            "total_time_steps": TOTAL_TIME_STEPS, "number_of_corrector_steps": 1,
+            "step": "one predictor-corrector iteration (2 EGNN forwards + updates) of the per-GPU batch; "
+                    "value = samples / (1000 x step time)",
+            "network": "EGNN 4 x E_GCL, hidden 256 x 4 (4,738,679 parameters), random init, rc 7.5 A",
+            "l2": "inputs larger than L2", "parallelism": f"samples sharded x{world}"}
 
 
 class ClockSampler:
@@ -184,16 +194,17 @@ def run_reference_arm(args, rank: int):
         return
     workload = args.workload
     samples = args.cpu_samples
-    seconds_per_step, cores = cpu_reference_run(workload, samples, args.steps, min(args.warmup, 1))
+    seconds_per_step, cores = cpu_reference_run(workload, samples, args.steps, args.warmup)
     value = samples / (TOTAL_TIME_STEPS * seconds_per_step)
     line = {
         "impl": "reference", "metric": "structures/sec", "value": value, "unit": "structures/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": seconds_per_step * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: {WORKLOADS[workload][0]}",
-                   "step": "one predictor-corrector iteration of the sample; a structure = 1000 steps"},
+        # the workload is the B200 arm's; each timed step processes a bounded sample of it (cpu_baseline.sample)
+        "config": workload_config(workload, args.samples or WORKLOADS[workload][5], 1),
         "cpu_baseline": {"value": value, "unit": "structures/s", "cores": cores, "kind": "port",
-                         "sample": f"{samples} structures x {args.steps} PC steps of T=1000, extrapolated linearly; "
+                         "sample": f"{samples} structures x {args.steps} PC steps of T=1000 (after {args.warmup} "
+                                   "warm-up steps), extrapolated linearly in the number of structures and steps; "
                                    "oracle/pc_oracle.py (torch CPU restatement of the reference; dense neighbour "
                                    "search stand-in for pykeops)"},
         "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,7 +256,7 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     generator.seed = 1234
     generator.sample_offset = rank * samples  # weak scaling: every rank owns `samples` structures
     K, W = args.steps, max(args.warmup, 3)
-    assert W + K <= TOTAL_TIME_STEPS
+    assert W + 2 * K + 5 <= TOTAL_TIME_STEPS
     if args.full_trajectory:
         run_full_trajectory(args, generator, network, samples, world, rank, device, description)
         return
@@ -276,12 +287,14 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
-    for _ in range(K):
-        composition = generator.sample_from_noisy_composition(composition, index, index - 1)
-        index -= 1
+    # the K timed steps are ONE call, as in production (generator.sample() hands the whole trajectory to
+    # b200md_pc_sample): no host synchronisation between steps
+    composition = generator.sample_from_noisy_composition(composition, index, index - K)
+    index -= K
     if world > 1:  # the single collective of the path: final all-gather of the sampled AXL
-        gathered = [torch.empty_like(composition.X) for _ in range(world)]
-        dist.all_gather(gathered, composition.X)
+        for part in (composition.A, composition.X, composition.L):
+            gathered = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(gathered, part.contiguous())
     stop.record()
     barrier()
     ms_total = max_over_ranks(start.elapsed_time(stop))
@@ -320,7 +333,7 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
         if rate is not None and executed_fraction is not None:
             ceiling = peak * rate / passes / executed_fraction
         roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((workload, samples, args.kernels)),
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "traffic_note": NCU_TRAFFIC_NOTE,
                     "peak_source": peaks["source"] + ": dense bf16/fp16, sustained",
                     "fp32_exact_passes": passes,
                     "fp32_exact_ceiling_tflops": ceiling,
@@ -341,7 +354,8 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     host_l = composition.L.cpu().pin_memory()
     out_x = torch.empty_like(host_x).pin_memory()
     out_a = torch.empty_like(host_a).pin_memory()
-    e2e_steps = min(K, 5)
+    e2e_steps = K
+    assert index - 1 - e2e_steps >= 0, "not enough time indices left for the end-to-end leg; lower --steps / --warmup"
 
     def e2e_step(idx):
         comp = AXL(A=host_a.to(device, non_blocking=True), X=host_x.to(device, non_blocking=True),
@@ -353,7 +367,7 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     e2e_step(index)
     barrier()
     start.record()
-    for k in range(e2e_steps):
+    for k in range(e2e_steps):   # every step: pinned host -> device, one PC step through the public API, device -> host
         e2e_step(index - 1 - k)
     stop.record()
     barrier()
@@ -376,13 +390,9 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
         "metric": "structures/sec", "value": value, "unit": "structures/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: {description}", "samples_per_gpu": samples, "atoms": atoms,
-                   "total_time_steps": TOTAL_TIME_STEPS, "number_of_corrector_steps": 1,
-                   "step": "one predictor-corrector iteration (2 EGNN forwards + updates) of the per-GPU batch; "
-                           "value = samples / (1000 x step time)",
-                   "network": "EGNN 4 x E_GCL, hidden 256 x 4 (4,738,679 parameters), random init, rc 7.5 A",
-                   "edge_mlp": network.last_edge_kernel_name(), "l2": "inputs larger than L2",
-                   "flop_per_structure_forward": flops["per_forward"], "parallelism": f"samples sharded x{world}"},
+        "config": workload_config(workload, samples, world),
+        "kernels": {"edge_mlp": network.last_edge_kernel_name(), "flop_per_structure_forward": flops["per_forward"],
+                    "loop": "one CUDA graph launch per PC step (b200md_pc_sample)"},
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }

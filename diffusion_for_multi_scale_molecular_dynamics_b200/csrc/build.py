@@ -13,7 +13,7 @@ import sys
 
 CSRC = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "elementwise.cu", "graph.cu", "structure.cu", "egnn.cu", "egnn_tc.cu", "egnn_node_tc.cu", "sampler.cu"]
-HEADERS = ["common.cuh", "graph.cuh", "egnn.cuh", "tc_common.cuh", "egnn_edge_ts.cuh", "ts_common.cuh", "egnn_node_ts.cuh", os.path.join("..", "..", "include", "b200md.h")]
+HEADERS = ["common.cuh", "graph.cuh", "egnn.cuh", "tc_common.cuh", "egnn_edge_ts.cuh", "ts_common.cuh", "egnn_node_ts.cuh", "sampler.cuh", os.path.join("..", "..", "include", "b200md.h")]
 LIBRARY = os.path.join(CSRC, "libb200md.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

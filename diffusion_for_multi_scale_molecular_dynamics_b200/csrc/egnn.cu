@@ -216,7 +216,7 @@ __device__ __forceinline__ void tile_linear(const float* in_s, int ld_in, float*
 // node kernel
 // ---------------------------------------------------------------------------------------------------
 struct NodeArgs {
-  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar;
+  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar; int sigma_stride;   // 1: sigma[sample]; 0: sigma[0] for every sample (one device-resident scalar)
   const float* packed;
   float *z, *xcur, *xagg, *h, *P, *Q, *agg;
   const int32_t* deg;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_kernel(NodeArgs a) {
       float v = 0.f;
       if (node < a.n_nodes) {
         const int64_t at = a.atom_types[node];
-        const float sg = a.sigma ? a.sigma[node / a.N] : a.sigma_scalar;
+        const float sg = a.sigma ? a.sigma[(node / a.N) * a.sigma_stride] : a.sigma_scalar;
         if (o == 0) {
           if (at < 0 || at >= a.C) local_status |= B200MD_STATUS_A_OUT_OF_RANGE;
           if (!(sg > 0.f)) local_status |= B200MD_STATUS_SIGMA_OUT_OF_RANGE;
@@ -533,7 +533,7 @@ static size_t edge_smem_bytes() {
 
 int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, const float* packed,
                       const int64_t* atom_types, const float* x, const float* lattice, const float* sigma,
-                      float sigma_scalar, int64_t B, int32_t N, int mask_logit, float* logits_out,
+                      float sigma_scalar, int sigma_stride, int64_t B, int32_t N, int mask_logit, float* logits_out,
                       float* score_out, const EgnnWorkspace& ws, int64_t edge_capacity, int32_t* status,
                       int impl, cudaStream_t st) {
   static PerDeviceOnce attrs;
@@ -571,7 +571,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
   if (rc != B200MD_OK) return rc;
 
   NodeArgs na{};
-  na.atom_types = atom_types; na.x_rel = x; na.sigma = sigma; na.sigma_scalar = sigma_scalar; na.packed = packed;
+  na.atom_types = atom_types; na.x_rel = x; na.sigma = sigma; na.sigma_scalar = sigma_scalar; na.sigma_stride = sigma_stride; na.packed = packed;
   na.z = ws.z; na.xcur = ws.xcur; na.xagg = ws.xagg; na.h = ws.h; na.P = ws.P; na.Q = ws.Q; na.agg = ws.agg;
   na.deg = ws.deg; na.logits_out = logits_out; na.score_out = score_out; na.status = status;
   na.n_nodes = BN; na.N = N;
@@ -586,7 +586,7 @@ int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, cons
   const unsigned node_grid = (unsigned)ceil_div64(BN, kTMN);
 
   NodeCall nc{};
-  nc.mask_logit = mask_logit; nc.atom_types = atom_types; nc.x_rel = x; nc.sigma = sigma; nc.sigma_scalar = sigma_scalar;
+  nc.mask_logit = mask_logit; nc.atom_types = atom_types; nc.x_rel = x; nc.sigma = sigma; nc.sigma_scalar = sigma_scalar; nc.sigma_stride = sigma_stride;
   nc.ws = &ws; nc.logits_out = logits_out; nc.score_out = score_out; nc.status = status; nc.n_nodes = BN; nc.n_atoms = N;
 
   // call 0: embedding + uplift + partial products of layer 0
@@ -775,7 +775,7 @@ int b200md_egnn_forward(const b200md_egnn_config* cfg, const float* packed, cons
   EgnnWorkspace ws;
   if (carve_workspace(*cfg, B, N, edge_capacity, workspace, ws) > workspace_bytes) return B200MD_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = as_stream(stream);
-  rc = egnn_forward_impl(*cfg, lay, packed, atom_types, x, lattice, sigma, 0.f, B, N, mask_logit, logits_out,
+  rc = egnn_forward_impl(*cfg, lay, packed, atom_types, x, lattice, sigma, 0.f, 1, B, N, mask_logit, logits_out,
                          score_out, ws, edge_capacity, status, impl, st);
   if (rc != B200MD_OK) return rc;
   if (n_edges_out) {

@@ -48,7 +48,7 @@ int64_t carve_workspace(const b200md_egnn_config& cfg, int64_t B, int32_t N, int
 
 int egnn_forward_impl(const b200md_egnn_config& cfg, const EgnnLayout& lay, const float* packed,
                       const int64_t* atom_types, const float* x, const float* lattice, const float* sigma,
-                      float sigma_scalar, int64_t B, int32_t N, int mask_logit, float* logits_out,
+                      float sigma_scalar, int sigma_stride, int64_t B, int32_t N, int mask_logit, float* logits_out,
                       float* score_out, const EgnnWorkspace& ws, int64_t edge_capacity, int32_t* status,
                       int impl, cudaStream_t st);
 
@@ -64,7 +64,7 @@ int tc_launch_edge_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, i
 // `pq_layer` (-1: none), read out.
 struct NodeCall {
   int embed, update_layer, pq_layer, readout, mask_logit;
-  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar;
+  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar; int sigma_stride;
   const EgnnWorkspace* ws;
   float* logits_out; float* score_out; int32_t* status;
   int64_t n_nodes; int32_t n_atoms;

@@ -22,7 +22,7 @@ struct NodeTcArgs {
   Program prog;
   int n_update;          // GEMMs of the node MLP in this call (0 when nothing is updated)
   int do_embed, do_update, do_pq, do_readout;
-  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar;
+  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar; int sigma_stride;
   float *z, *xcur, *xagg, *h, *P, *Q, *agg;
   const int32_t* deg;
   float* logits_out; float* score_out; int32_t* status;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
       int atc = 0;
       if (a.do_embed && valid) {
         const int64_t at = a.atom_types[node];
-        sg = a.sigma ? a.sigma[node / a.n_atoms] : a.sigma_scalar;
+        sg = a.sigma ? a.sigma[(node / a.n_atoms) * a.sigma_stride] : a.sigma_scalar;
         if (hh == 0) {
           if (at < 0 || at >= a.C) local_status |= B200MD_STATUS_A_OUT_OF_RANGE;
           if (!(sg > 0.f)) local_status |= B200MD_STATUS_SIGMA_OUT_OF_RANGE;
@@ -355,7 +355,7 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
   }
   p.n_gemms = g;
   a.do_embed = call.embed; a.do_update = call.update_layer >= 0; a.do_pq = call.pq_layer >= 0; a.do_readout = call.readout;
-  a.atom_types = call.atom_types; a.x_rel = call.x_rel; a.sigma = call.sigma; a.sigma_scalar = call.sigma_scalar;
+  a.atom_types = call.atom_types; a.x_rel = call.x_rel; a.sigma = call.sigma; a.sigma_scalar = call.sigma_scalar; a.sigma_stride = call.sigma_stride;
   a.z = call.ws->z; a.xcur = call.ws->xcur; a.xagg = call.ws->xagg; a.h = call.ws->h; a.P = call.ws->P; a.Q = call.ws->Q;
   a.agg = call.ws->agg; a.deg = call.ws->deg;
   a.logits_out = call.logits_out; a.score_out = call.score_out; a.status = call.status;
@@ -396,7 +396,7 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
     }
     t.n_gemms = n;
     t.do_embed = call.embed; t.do_update = call.update_layer >= 0; t.do_readout = call.readout;
-    t.atom_types = call.atom_types; t.x_rel = call.x_rel; t.sigma = call.sigma; t.sigma_scalar = call.sigma_scalar;
+    t.atom_types = call.atom_types; t.x_rel = call.x_rel; t.sigma = call.sigma; t.sigma_scalar = call.sigma_scalar; t.sigma_stride = call.sigma_stride;
     t.z = call.ws->z; t.xcur = call.ws->xcur; t.xagg = call.ws->xagg; t.h = call.ws->h; t.agg = call.ws->agg;
     t.U = call.ws->U; t.deg = call.ws->deg;
     t.logits_out = call.logits_out; t.score_out = call.score_out; t.status = call.status;

@@ -44,7 +44,7 @@ struct NodeTsArgs {
   int n_gemms;
   NodeTsGemm g[kMaxGemms];
   int do_embed, do_update, do_readout;
-  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar;
+  const int64_t* atom_types; const float* x_rel; const float* sigma; float sigma_scalar; int sigma_stride;
   float *z, *xcur, *xagg, *h, *agg;
   const float* U;
   const int32_t* deg;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       int atc = 0;
       if (a.do_embed && valid) {
         const int64_t at = a.atom_types[node];
-        sg = a.sigma ? a.sigma[node / a.n_atoms] : a.sigma_scalar;
+        sg = a.sigma ? a.sigma[(node / a.n_atoms) * a.sigma_stride] : a.sigma_scalar;
         if (part == 0) {
           if (at < 0 || at >= a.C) local_status |= B200MD_STATUS_A_OUT_OF_RANGE;
           if (!(sg > 0.f)) local_status |= B200MD_STATUS_SIGMA_OUT_OF_RANGE;

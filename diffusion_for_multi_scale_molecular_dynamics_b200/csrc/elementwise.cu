@@ -4,6 +4,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "sampler.cuh"
 
 namespace b200md {
 
@@ -87,12 +88,23 @@ __device__ __forceinline__ float pc_update_value(float x, float s, float z, floa
   return wrap_unit(__fadd_rn(__fadd_rn(x, a), b));
 }
 
+// step-dependent arguments of a graph-replayed launch (sampler.cuh)
+__device__ __forceinline__ void pc_step_weights(const PcStepScalars* cur, int phase, float& sw, float& sigma, float& nw,
+                                                uint32_t& step_id) {
+  const bool predictor = phase == 0;
+  sw = predictor ? cur->g2 : cur->eps;
+  sigma = predictor ? cur->sigma_pred : cur->sigma_corr;
+  nw = predictor ? cur->g : cur->sqrt_2eps;
+  step_id = cur->step_id + (uint32_t)phase;
+}
+
 template <int D>
 __global__ void pc_coordinates_update_kernel(const float* x, const float* __restrict__ s,
                                              const float* __restrict__ z, float sw, float sigma,
                                              float nw, int64_t n_samples, int32_t n_atoms,
                                              uint64_t seed, uint32_t step_id,
-                                             uint64_t sample_offset, float* out) {
+                                             uint64_t sample_offset, float* out, const PcStepScalars* cur, int phase) {
+  if (cur != nullptr) pc_step_weights(cur, phase, sw, sigma, nw, step_id);
   const int64_t total = n_samples * n_atoms;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -121,7 +133,8 @@ __global__ void pc_coordinates_update_kernel(const float* x, const float* __rest
 __global__ void pc_coordinates_update_v4_kernel(const float4* x, const float4* __restrict__ s,
                                                 const float4* __restrict__ z, float sw, float sigma, float nw,
                                                 int64_t n_groups, int32_t n_atoms, uint64_t seed, uint32_t step_id,
-                                                uint64_t sample_offset, float4* out) {
+                                                uint64_t sample_offset, float4* out, const PcStepScalars* cur, int phase) {
+  if (cur != nullptr) pc_step_weights(cur, phase, sw, sigma, nw, step_id);
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
        g += (int64_t)gridDim.x * blockDim.x) {
     float xv[12], sv[12], zv[12];
@@ -270,7 +283,14 @@ __global__ void atom_types_update_kernel(const float* __restrict__ logits, const
                                          int32_t flags, float eps, int32_t n_atoms, int32_t C,
                                          uint64_t seed, uint32_t step_id, uint64_t sample_offset,
                                          int64_t* a_out, float* __restrict__ probs_out,
-                                         int32_t* __restrict__ status) {
+                                         int32_t* __restrict__ status, const PcStepScalars* cur, int phase) {
+  if (cur != nullptr) {   // graph replay: flags, table rows and the draw key of THIS step (sampler.cuh)
+    const bool predictor = phase == 0;
+    flags = predictor ? cur->atom_flags_pred : cur->atom_flags_corr;
+    const int64_t row = (int64_t)(predictor ? cur->q_index_pred : cur->q_index_corr) * C * C;
+    q += row; qbar += row; qbar_tm1 += row;
+    step_id = cur->step_id + (uint32_t)phase;
+  }
   extern __shared__ unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);  // [3][C*C]
   float* s_best = s_q + 3 * C * C;                  // [n_atoms]  winning Gumbel value
@@ -421,7 +441,12 @@ __global__ void repaint_kernel(float* __restrict__ x, int64_t* __restrict__ a, c
                                int32_t nc, float sigma_i, const float* __restrict__ qbar,
                                const float* __restrict__ z, const float* __restrict__ u,
                                int64_t n_samples, int32_t n_atoms, int32_t D, int32_t C, uint64_t seed,
-                               uint32_t step_id, uint64_t sample_offset) {
+                               uint32_t step_id, uint64_t sample_offset, const PcStepScalars* cur) {
+  if (cur != nullptr) {   // graph replay (sampler.cuh)
+    sigma_i = cur->repaint_sigma;
+    if (cur->q_index_repaint >= 0) qbar += (int64_t)cur->q_index_repaint * C * C;
+    step_id = cur->step_id;
+  }
   const int64_t total = n_samples * nc;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -634,6 +659,74 @@ static inline unsigned grid_for(int64_t total, int threads) {
   return (unsigned)b;
 }
 
+int pc_coordinates_update_impl(const float* x, const float* s, const float* z, float score_weight, float sigma,
+                               float noise_weight, int64_t n_samples, int32_t n_atoms, int32_t D, uint64_t seed,
+                               uint32_t step_id, uint64_t sample_offset, float* x_out, const PcStepScalars* cur,
+                               int phase, cudaStream_t st) {
+  if (n_samples == 0) return B200MD_OK;
+  if (!x || !s || !x_out || n_samples < 0 || n_atoms <= 0 || D < 1 || D > 3)
+    return B200MD_ERR_INVALID_ARGUMENT;
+  const int64_t total = n_samples * n_atoms;
+  const unsigned g = grid_for(total, 256);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(z) |
+                         reinterpret_cast<uintptr_t>(x_out)) & 15u) == 0;
+  if (D == 3 && (total & 3) == 0 && aligned) {
+    ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
+    pc_coordinates_update_v4_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(z),
+        score_weight, sigma, noise_weight, total / 4, n_atoms, seed, step_id, sample_offset, reinterpret_cast<float4*>(x_out),
+        cur, phase);
+  } else {
+    ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
+    switch (D) {
+      case 1: pc_coordinates_update_kernel<1><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out, cur, phase); break;
+      case 2: pc_coordinates_update_kernel<2><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out, cur, phase); break;
+      default: pc_coordinates_update_kernel<3><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out, cur, phase); break;
+    }
+  }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int atom_types_update_impl(const float* logits, const int64_t* atom_types, const float* q, const float* q_bar,
+                           const float* q_bar_tm1, const float* gumbel, const float* binary, int32_t flags,
+                           float small_epsilon, int64_t n_samples, int32_t n_atoms, int32_t n_classes, uint64_t seed,
+                           uint32_t step_id, uint64_t sample_offset, int64_t* atom_types_out, float* probs_out,
+                           int32_t* status, const PcStepScalars* cur, int phase, cudaStream_t st) {
+  if (!logits || !atom_types || !q || !q_bar || !q_bar_tm1 || !atom_types_out || n_samples < 0 ||
+      n_atoms <= 0 || n_classes < 2)
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_classes > kMaxClasses) return B200MD_ERR_UNSUPPORTED;
+  if (n_samples == 0) return B200MD_OK;
+  int threads = ((n_atoms + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  size_t smem = (size_t)3 * n_classes * n_classes * sizeof(float) + (size_t)n_atoms * 8;
+  if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(atom_types_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); atom_types_update_kernel<<<(unsigned)n_samples, threads, smem, st>>>(
+      logits, atom_types, q, q_bar, q_bar_tm1, gumbel, binary, flags, small_epsilon, n_atoms, n_classes,
+      seed, step_id, sample_offset, atom_types_out, probs_out, status, cur, phase); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int repaint_impl(float* x, int64_t* atom_types, const float* x0_known, const int64_t* a0_known,
+                 const int64_t* constrained_indices, int32_t n_constrained, float sigma_i, const float* q_bar,
+                 const float* z, const float* u, int64_t n_samples, int32_t n_atoms, int32_t D, int32_t n_classes,
+                 uint64_t seed, uint32_t step_id, uint64_t sample_offset, const PcStepScalars* cur, cudaStream_t st) {
+  if (!x || !atom_types || !x0_known || !a0_known || n_constrained < 0 || n_samples < 0 || D < 1 ||
+      D > 3 || ((cur != nullptr || sigma_i >= 0.f) && !q_bar))
+    return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0 || n_constrained == 0) return B200MD_OK;
+  const int64_t total = n_samples * n_constrained;
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); repaint_kernel<<<grid_for(total, 128), 128, 0, st>>>(
+      x, atom_types, x0_known, a0_known, constrained_indices, n_constrained, sigma_i, q_bar, z, u,
+      n_samples, n_atoms, D, n_classes, seed, step_id, sample_offset, cur); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
 }  // namespace b200md
 
 using namespace b200md;
@@ -677,29 +770,8 @@ int b200md_pc_coordinates_update(const float* x, const float* s, const float* z,
                                  float sigma, float noise_weight, int64_t n_samples, int32_t n_atoms,
                                  int32_t D, uint64_t seed, uint32_t step_id, uint64_t sample_offset,
                                  float* x_out, b200md_stream_t stream) {
-  if (n_samples == 0) return B200MD_OK;
-  if (!x || !s || !x_out || n_samples < 0 || n_atoms <= 0 || D < 1 || D > 3)
-    return B200MD_ERR_INVALID_ARGUMENT;
-  const int64_t total = n_samples * n_atoms;
-  const unsigned g = grid_for(total, 256);
-  cudaStream_t st = as_stream(stream);
-  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(z) |
-                         reinterpret_cast<uintptr_t>(x_out)) & 15u) == 0;
-  if (D == 3 && (total & 3) == 0 && aligned) {
-    ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
-    pc_coordinates_update_v4_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(z),
-        score_weight, sigma, noise_weight, total / 4, n_atoms, seed, step_id, sample_offset, reinterpret_cast<float4*>(x_out));
-  } else {
-    ProfileScope ps__(B200MD_KERNEL_UPDATE, st);
-    switch (D) {
-      case 1: pc_coordinates_update_kernel<1><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
-      case 2: pc_coordinates_update_kernel<2><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
-      default: pc_coordinates_update_kernel<3><<<g, 256, 0, st>>>(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, seed, step_id, sample_offset, x_out); break;
-    }
-  }
-  B200MD_CHECK_LAUNCH();
-  return B200MD_OK;
+  return pc_coordinates_update_impl(x, s, z, score_weight, sigma, noise_weight, n_samples, n_atoms, D, seed, step_id,
+                                    sample_offset, x_out, nullptr, 0, as_stream(stream));
 }
 
 int b200md_adaptive_corrector_step_size(const float* s, const float* z, int64_t n_samples, int32_t units, int32_t d,
@@ -745,22 +817,9 @@ int b200md_atom_types_update(const float* logits, const int64_t* atom_types, con
                              int64_t n_samples, int32_t n_atoms, int32_t n_classes, uint64_t seed,
                              uint32_t step_id, uint64_t sample_offset, int64_t* atom_types_out,
                              float* probs_out, int32_t* status, b200md_stream_t stream) {
-  if (!logits || !atom_types || !q || !q_bar || !q_bar_tm1 || !atom_types_out || n_samples < 0 ||
-      n_atoms <= 0 || n_classes < 2)
-    return B200MD_ERR_INVALID_ARGUMENT;
-  if (n_classes > kMaxClasses) return B200MD_ERR_UNSUPPORTED;
-  if (n_samples == 0) return B200MD_OK;
-  int threads = ((n_atoms + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  size_t smem = (size_t)3 * n_classes * n_classes * sizeof(float) + (size_t)n_atoms * 8;
-  if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(atom_types_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  { ProfileScope ps__(B200MD_KERNEL_UPDATE, as_stream(stream)); atom_types_update_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
-      logits, atom_types, q, q_bar, q_bar_tm1, gumbel, binary, flags, small_epsilon, n_atoms, n_classes,
-      seed, step_id, sample_offset, atom_types_out, probs_out, status); }
-  B200MD_CHECK_LAUNCH();
-  return B200MD_OK;
+  return atom_types_update_impl(logits, atom_types, q, q_bar, q_bar_tm1, gumbel, binary, flags, small_epsilon, n_samples,
+                                n_atoms, n_classes, seed, step_id, sample_offset, atom_types_out, probs_out, status,
+                                nullptr, 0, as_stream(stream));
 }
 
 int b200md_repaint(float* x, int64_t* atom_types, const float* x0_known, const int64_t* a0_known,
@@ -768,16 +827,8 @@ int b200md_repaint(float* x, int64_t* atom_types, const float* x0_known, const i
                    const float* q_bar_i, const float* z, const float* u, int64_t n_samples,
                    int32_t n_atoms, int32_t D, int32_t n_classes, uint64_t seed, uint32_t step_id,
                    uint64_t sample_offset, b200md_stream_t stream) {
-  if (!x || !atom_types || !x0_known || !a0_known || n_constrained < 0 || n_samples < 0 || D < 1 ||
-      D > 3 || (sigma_i >= 0.f && !q_bar_i))
-    return B200MD_ERR_INVALID_ARGUMENT;
-  if (n_samples == 0 || n_constrained == 0) return B200MD_OK;
-  const int64_t total = n_samples * n_constrained;
-  { ProfileScope ps__(B200MD_KERNEL_UPDATE, as_stream(stream)); repaint_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
-      x, atom_types, x0_known, a0_known, constrained_indices, n_constrained, sigma_i, q_bar_i, z, u,
-      n_samples, n_atoms, D, n_classes, seed, step_id, sample_offset); }
-  B200MD_CHECK_LAUNCH();
-  return B200MD_OK;
+  return repaint_impl(x, atom_types, x0_known, a0_known, constrained_indices, n_constrained, sigma_i, q_bar_i, z, u,
+                      n_samples, n_atoms, D, n_classes, seed, step_id, sample_offset, nullptr, as_stream(stream));
 }
 
 int b200md_wrapped_gaussian_score_f32(const float* u, const float* sigma, int64_t n, int32_t kmax,

@@ -373,11 +373,15 @@ int b200md_egnn_forward(const b200md_egnn_config* cfg, const float* packed,
  * (generators/predictor_corrector_axl_generator.py:112-161) driving LangevinGenerator.predictor_step /
  * corrector_step (generators/langevin_generator.py:536-645,693-805) with the EGNN score network, every
  * launch enqueued from one host call, noise drawn in-kernel, no host synchronisation.
+ * One predictor-corrector step (~27 kernels) is captured into a CUDA graph that reads its step-dependent scalars
+ * from a device table (csrc/sampler.cuh) and is replayed once per time index; trajectories longer than
+ * B200MD_PC_MAX_GRAPH_STEPS steps, B200MD_PC_DIRECT=1 in the environment, or per-class profiling use direct launches.
  * Schedule tables are DEVICE arrays from NoiseScheduler (noise_schedulers/noise_scheduler.py:348-378):
  * sigma,g,g2 [T]; epsilon [T]; q,q_bar,q_bar_tm1 [T,C,C]; the host copies `*_host` [T] drive kernel arguments.
  * In place on atom_types [B,N], x [B,N,3]; lattice [B,6] is fixed (use_fixed_lattice_parameters=True).
  * Optional constraint (RePaint, constrained_langevin_generator.py) when n_constrained > 0.
  * ---------------------------------------------------------------------------------------------- */
+#define B200MD_PC_MAX_GRAPH_STEPS 4096   /* rows of the device-side step table in the sampler workspace (64 B each) */
 typedef struct {
   int32_t total_time_steps;           /* T */
   int32_t number_of_corrector_steps;
@@ -407,7 +411,7 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed,
                      const float* lattice, int64_t n_samples, int32_t n_atoms, uint64_t seed,
                      uint64_t sample_offset, void* workspace, int64_t workspace_bytes,
                      int64_t edge_capacity, int32_t* status, int32_t impl, b200md_stream_t stream);
-/* extra workspace b200md_pc_sample needs on top of b200md_egnn_workspace_bytes */
+/* whole workspace of b200md_pc_sample: b200md_egnn_workspace_bytes + logits + scores + the device-side step table */
 int64_t b200md_pc_sample_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_samples,
                                          int32_t n_atoms, int64_t edge_capacity);
 

@@ -46,7 +46,12 @@ def test_egnn_degenerate_graphs(cuda_device, B, N, edges, impl):
     sigma = torch.rand(B, 1) * 0.3 + 0.01
     net, out, (logits32, score32, logits64, score64) = forward_both(cuda_device, hp, a, x, lattice, sigma, impl)
     assert_anchored(out.A, logits32, logits64, "logits")
-    assert_anchored(out.X, score32, score64, "score")
+    if N == 1:
+        # no edge: zhat = z and S = z . Gamma . z is exactly 0; what the kernel returns is the rounding residue of one
+        # fused multiply-add on products of unit-size numbers (c s - s c), at most one ulp of those products
+        assert float(score64.abs().max()) == 0.0 and float(out.X.abs().max()) <= 2.0 ** -23
+    else:
+        assert_anchored(out.X, score32, score64, "score")
     if (B, N) == (64, 2):
         assert net.last_number_of_edges() == 128
     if N == 1:

@@ -70,3 +70,27 @@ def test_fused_loop_equals_step_by_step(cuda_device, n_corr, start, end):
     stepped = gen.sample_from_noisy_composition(make(), start, end)
     assert torch.equal(fused.A, stepped.A)
     assert torus_distance(fused.X, stepped.X).max() < 2e-5
+
+
+@pytest.mark.parametrize("n_corr,start,end", [(1, T, 0), (2, 5, 1)])
+def test_graph_replay_equals_direct_launches(cuda_device, n_corr, start, end, monkeypatch):
+    """b200md_pc_sample replays ONE captured step graph whose kernels read their step scalars from a device table
+    (csrc/sampler.cu); B200MD_PC_DIRECT=1 enqueues the same kernels one by one with the scalars as launch arguments.
+    Same kernels, same arguments: same atom types, coordinates equal up to the order of the fp32 atomics."""
+    gen, _, x0, lattice = setup(cuda_device, n_corr)
+    gen.seed = 31
+    a0 = torch.full((B, N), 2)
+    make = lambda: AXL(A=a0.clone().to(cuda_device), X=x0.clone().to(cuda_device), L=lattice.to(cuda_device))  # noqa: E731
+    from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+    before = _cabi.launch_count()
+    replayed = gen.sample_from_noisy_composition(make(), start, end)
+    launches_graph = _cabi.launch_count() - before
+    monkeypatch.setenv("B200MD_PC_DIRECT", "1")
+    before = _cabi.launch_count()
+    direct = gen.sample_from_noisy_composition(make(), start, end)
+    launches_direct = _cabi.launch_count() - before
+    assert torch.equal(replayed.A, direct.A)
+    assert torus_distance(replayed.X, direct.X).max() < 2e-5
+    assert not torch.equal(replayed.X.cpu(), x0)
+    # the launch counter counts kernels executed: the graph adds its table loader and one cursor kernel per step
+    assert launches_graph == launches_direct + 1 + (start - end)
