@@ -260,6 +260,9 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     if args.full_trajectory:
         run_full_trajectory(args, generator, network, samples, world, rank, device, description)
         return
+    if args.strong:
+        run_strong(args, generator, network, noise, sampling, world, rank, local_rank, device)
+        return
 
     def barrier():
         if world > 1:
@@ -399,6 +402,77 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def run_strong(args, generator, network, noise, sampling, world, rank, local_rank, device):
+    """Strong scaling through the product shard point: ``create_batch_of_samples`` (sampling/diffusion_sampling.py)
+    draws a FIXED total number of samples (the configuration as BASELINE states it: 4096 for cfg2, 8192 for cfg5),
+    sharded over the ranks by ``shard_range`` with the counter-based noise keyed by the global sample index, and
+    gathers (A, X, L) on every rank with NCCL at the end.  To keep the run bounded the trajectory is the last K steps of
+    the T = 1000 schedule (time indices K .. 1, started from a fresh random configuration): per-step work is the
+    production step's; value = total samples / (1000 x time per step)."""
+    import torch.distributed as dist
+
+    from diffusion_for_multi_scale_molecular_dynamics_b200.generators.trajectory_initializer import \
+        FullRandomTrajectoryInitializer
+    from diffusion_for_multi_scale_molecular_dynamics_b200.namespace import AXL_COMPOSITION
+    from diffusion_for_multi_scale_molecular_dynamics_b200.sampling.diffusion_sampling import create_batch_of_samples
+
+    total = args.samples or {"cfg5": 8192}.get(args.workload, WORKLOADS[args.workload][5])
+    K, W = args.steps, max(args.warmup, 3)
+    steps_to_run = {"n": W}
+
+    class LastSteps(type(generator.trajectory_initializer)):
+        def create_start_time_step_index(self, number_of_discretization_steps: int) -> int:
+            return steps_to_run["n"]
+
+    assert isinstance(generator.trajectory_initializer, FullRandomTrajectoryInitializer)
+    generator.trajectory_initializer.__class__ = LastSteps
+    generator.sample_offset = 0
+    sampling.number_of_samples = total
+    sampling.sample_batchsize = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    create_batch_of_samples(generator, sampling, device)   # warm-up: W steps, packing, workspace, NCCL channels
+    steps_to_run["n"] = K
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+    launches_before = _cabi.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    batch = create_batch_of_samples(generator, sampling, device)
+    stop.record()
+    barrier()
+    ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = _cabi.launch_count() - launches_before
+    clocks = sampler.stop() if sampler is not None else None
+    axl = batch[AXL_COMPOSITION]
+    assert axl.X.shape[0] == total and axl.A.shape[0] == total and axl.L.shape[0] == total
+    if rank != 0:
+        return
+    ms_per_step = ms / K
+    config = workload_config(args.workload, None, world)
+    config.update(samples_total=total, samples_per_gpu=f"{total} / {world}",
+                  trajectory=f"last {K} steps of the T=1000 schedule through create_batch_of_samples, incl. "
+                             "initialisation and the final NCCL all_gather of (A, X, L)")
+    print(json.dumps({
+        "metric": "structures/sec", "value": total / (TOTAL_TIME_STEPS * ms_per_step * 1e-3), "unit": "structures/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "kernels": {"edge_mlp": network.last_edge_kernel_name()}, "gpu_launches": int(launches), "clocks": clocks,
+        "all_unmasked": bool((axl.A != generator.masked_atom_type_index).all()),
+        "gathered_bytes_per_rank": int(axl.X[: total // world].numel() * 4 + axl.A[: total // world].numel() * 8
+                                       + axl.L[: total // world].numel() * 4)}), flush=True)
+
+
 def run_full_trajectory(args, generator, network, samples, world, rank, device, description):
     """Validation of the per-step extrapolation: time generator.sample() -- initialisation, all 1000 steps, final
     device->host copy -- for `samples` structures per GPU and report structures/sec directly."""
@@ -462,6 +536,9 @@ def main():
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--full-trajectory", action="store_true",
                         help="time one complete generator.sample() of --samples structures instead of K steps")
+    parser.add_argument("--strong", action="store_true",
+                        help="strong scaling: a fixed TOTAL number of samples (--samples, default the configuration's: "
+                             "4096 for cfg2, 8192 for cfg5) sharded over the ranks by create_batch_of_samples")
     parser.add_argument("--kernels", choices=["auto", "ffma", "tf32x3", "f16x3", "f16x3ts"], default="auto",
                         help="edge/node MLP implementation (auto = what the library picks for the configuration)")
     args = parser.parse_args()

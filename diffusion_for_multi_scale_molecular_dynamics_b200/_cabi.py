@@ -167,6 +167,7 @@ SIGNATURES = {
          c_int32, _P],
     ),
     "b200md_pc_sample_workspace_bytes": (c_int64, [_CFG, c_int64, c_int32, c_int64]),
+    "b200md_pc_sample_last_mode": (c_int32, []),
 }
 
 _LIB: Optional[ctypes.CDLL] = None

@@ -17,7 +17,7 @@
 //
 // Warps (10): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue: two per TMEM lane quarter,
 // each converting 32 of the 64 columns of a chunk (few, fat epilogue threads: 168 registers each, 32 independent SiLU
-// chains per thread for the SFU pipe).
+// chains per thread for the SFU pipe).  (ts_common.cuh: B200MD_TS_WARPGROUPS for the 12-warp setmaxnreg layout.)
 #pragma once
 
 #include "ts_common.cuh"
@@ -111,6 +111,11 @@ struct TsPipe {
   }
 };
 
+// B200MD_TS_PQ_AHEAD = 1 requests the P / Q rows of the next tile one chunk ahead of their use (needs the registers of
+// B200MD_TS_WARPGROUPS = 1); measured slower, see ts_common.cuh.
+#ifndef B200MD_TS_PQ_AHEAD
+#define B200MD_TS_PQ_AHEAD 0
+#endif
 __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -167,6 +172,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   if (blockIdx.x == 0 && threadIdx.x == 0) g_ts_trace_count = kTsTraceMax;
 #endif
 
+  // setmaxnreg sits at the top of each warpgroup's branch: ptxas budgets the code a setmaxnreg dominates (after a merge
+  // of the two branches it would compile everything for the smaller value)
+  if (warp < kTsFirstEpiWarp) {
+#if B200MD_TS_WARPGROUPS
+  ts_regs_release<kTsRegsControl>();
+#endif
   if (warp == 0) {
     // ===== weight producer =====
     if (lane == 0) {
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               tc_fence_after();
               if (leader) {
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);   // A_1 B_1
-                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescNegateA, 1u);   // A_2 B_1 (A_2 is stored negated)
+                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescA2, 1u);   // A_2 B_1 (A_2 is stored negated)
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);             // A_1 B_2
               }
             }
@@ -252,10 +263,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         }
         mca += nk;
       }
+  }
   } else {
+#if B200MD_TS_WARPGROUPS
+    ts_regs_acquire<kTsRegsEpilogue>();
+#endif
     // ===== epilogue warps =====
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int part = (warp - 2) >> 2;         // which kTsCols columns of a chunk this warp converts
+    const int part = (warp - kTsFirstEpiWarp) >> 2;   // which kTsCols columns of a chunk this warp converts
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = pipe.tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t sa_bias = pipe.s_base + L.bias, sa_wr = pipe.s_base + L.wr, sa_wlast = pipe.s_base + L.wlast;
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     // (warp-uniform branch on the tails mask).  8 st.shared.v4 + 32 ld.shared per thread instead of 160 shuffles and
     // 160 selects / adds (the shuffles use the same crossbar as shared memory): the message layer's period drops from
     // 21.3 k to 13.0 k cycles (other layers: 8.9 k) and the launch from 19.44 to 18.98 ms (A/B on one box).
-    const uint32_t seg_tile = pipe.s_base + L.seg + (uint32_t)(warp - 2) * kTsSegTileBytes;
+    const uint32_t seg_tile = pipe.s_base + L.seg + (uint32_t)(warp - kTsFirstEpiWarp) * kTsSegTileBytes;
     const uint32_t seg_read = seg_tile + (uint32_t)(lane & 3) * 4u;
     auto segment_add = [&](const Edge& ed, const float (&v)[kTsCols], float* target, int ld, int col0) {
 #pragma unroll
@@ -379,6 +394,42 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         prefetch_l1(qq);
       }
 #endif
+    };
+    // The gathered rows P[src], Q[dst] of one chunk (kTsCols columns each).  At the tile boundary they are requested one
+    // chunk ahead of their use (load_pq), so the L2 round trip of the gather runs under the SiLU / dot-product work
+    // of the current tile's last layer instead of in front of the next tile's first MMA (the cycle trace showed 19.6 k
+    // cycles for that layer against 8.9 k for a plain one).
+    struct PQ {
+      float4 p[kTsCols / 4], q[kTsCols / 4];
+    };
+    auto load_pq = [&](const Edge& ed, int c, PQ& t) {
+      if (ed.valid) {
+        const int col0 = c * 64 + part * kTsCols;
+        const float4* p4 = reinterpret_cast<const float4*>(a.P + (int64_t)ed.src * M + col0);
+        const float4* q4 = reinterpret_cast<const float4*>(a.Q + (int64_t)ed.dst * M + col0);
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) { t.p[j] = __ldg(p4 + j); t.q[j] = __ldg(q4 + j); }
+      }
+    };
+    auto first_activation_from = [&](const Edge& ed, int c, uint32_t a_col, const PQ& t) {
+      const int col0 = c * 64 + part * kTsCols;
+      float v[kTsCols];
+      if (ed.valid) {
+        const uint64_t rad2 = pack2(ed.radial, ed.radial);
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) {
+          const float4 pv = t.p[j], qv = t.q[j], wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
+          silu2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), v[4 * j + 0], v[4 * j + 1]);
+          silu2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
+      }
+      if (a.n_msg == 0) segment_add(ed, v, a.agg, M, col0);  // no hidden layer: this IS the message
+      uint32_t w[kTsCols];
+      split_hi_lo(v, w);
+      publish(a_col + (uint32_t)col0, w);
     };
     auto first_activation_chunk = [&](const Edge& ed, int c, uint32_t a_col) {
       const int col0 = c * 64 + part * kTsCols;
@@ -517,6 +568,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             }
           }
         } else {
+#if B200MD_TS_PQ_AHEAD
+          PQ ahead;
+          if (has_next) load_pq(next, 0, ahead);
+#endif
           for (int c = 0; c < nchunks; ++c) {
             wait_for_chunk(c);
             const int col0 = c * 64 + part * kTsCols;
@@ -536,14 +591,24 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             // these accumulator columns are free now: the next tile's first activation goes there IN PLACE, so its
             // first GEMM starts while this tile is being finished
             if (has_next && c < nk0) {
+#if B200MD_TS_PQ_AHEAD
+              first_activation_from(next, c, d_col, ahead);
+              if (c + 1 < nk0) load_pq(next, c + 1, ahead);   // used after the next chunk's SiLU and dot product
+#else
               if (c + 1 < nk0) prefetch_first(next, c + 1);
               first_activation_chunk(next, c, d_col);
+#endif
             }
           }
           if (has_next)
             for (int c = n_last; c < nk0; ++c) {   // message width > coordinate width: columns no accumulator used
+#if B200MD_TS_PQ_AHEAD
+              first_activation_from(next, c, d_col, ahead);
+              if (c + 1 < nk0) load_pq(next, c + 1, ahead);
+#else
               if (c + 1 < nk0) prefetch_first(next, c + 1);
               first_activation_chunk(next, c, d_col);
+#endif
             }
         }
       }

@@ -14,8 +14,8 @@
 // the edge kernel); the three output GEMMs keep h' in one buffer and reuse the other as accumulator, so each waits for
 // the epilogue to have drained the previous one ("d_free").
 //
-// Warps (10): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue (two per TMEM lane quarter,
-// 32 columns per thread and chunk).
+// Warps (10; ts_common.cuh): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue (two per TMEM
+// lane quarter, 32 columns per thread and chunk).
 #pragma once
 
 #include "ts_common.cuh"
@@ -30,8 +30,9 @@ enum NodeGemmKind {
 struct NodeTsGemm {
   int K, N, kind;
   int fresh_a;          // the MMA waits for the epilogue to publish the A chunks (else: same A as the previous GEMM)
-  int wait_d_free;      // the accumulator buffer still holds the previous output: wait until the epilogue drained it
-  int signal_d_free;    // ... and the epilogue says so after draining this one
+  int wait_d_free;      // the accumulator buffer still holds the previous output: each column group waits until the
+                        // epilogue has drained that group (so the MMAs of one output run under the drain of the previous)
+  int signal_d_free;    // ... and the epilogue says so, group by group, while draining this one
   int64_t w16;          // offset (floats) in wtc of the fp16 image of the first K chunk
   int64_t unscale;      // offset in wtc of 2^-s: the image holds 2^s w (tc_common.cuh), the epilogue multiplies it back
   int64_t bias;         // offset in packed, or -1
@@ -64,7 +65,7 @@ __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   NodeTsSmem L;
   uint32_t o = 0;
   L.b = o; o += kTsBStages * kTsBStageBytes;
-  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit + 1) * 8;
+  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit + kTsNSplit) * 8;
   L.tmem_slot = o; o += 16;
   o = (o + 15u) & ~15u;   // the bias rows are read with 128-bit shared loads
   L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
@@ -85,7 +86,10 @@ struct NodeTsBars {
   __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
     return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
   }
-  __device__ __forceinline__ uint32_t d_free() const { return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit); }
+  // "column group `group` of the output accumulator has been drained"
+  __device__ __forceinline__ uint32_t d_free(uint32_t group) const {
+    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit + group);
+  }
 };
 
 __device__ __forceinline__ void load_cols(const float* p, float (&v)[kTsCols]) {
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(bars.a_full(s, j), 4);
     for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(bars.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
-    mbar_init(bars.d_free(), kTsEpiWarps);
+    for (int s = 0; s < kTsNSplit; ++s) mbar_init(bars.d_free(s), kTsEpiWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_base + L.tmem_slot, kTmemCols);
@@ -138,6 +142,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
   const uint32_t tmem_base_all = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
   const int n_iterations = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+  if (warp < kTsFirstEpiWarp) {   // setmaxnreg at the top of each warpgroup's branch (see egnn_edge_ts.cuh)
+#if B200MD_TS_WARPGROUPS
+  ts_regs_release<kTsRegsControl>();
+#endif
   if (warp == 0) {
     // ===== weight producer =====
     if (lane == 0) {
@@ -173,8 +181,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         const int nk = G.K / 64, nh = G.N / kTsNSplit;
         const uint32_t idesc = make_idesc(nh, 0u);
         const uint32_t a_col = abuf * kMaxN, d_col = a_col ^ kMaxN;
-        if (G.wait_d_free) { mbar_wait(bars.d_free(), df & 1u); ++df; tc_fence_after(); }
         for (int h = 0; h < kTsNSplit; ++h) {
+          if (G.wait_d_free) { mbar_wait(bars.d_free(h), df & 1u); tc_fence_after(); }
           const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
           for (int c = 0; c < nk; ++c) {
             const uint32_t s1 = cb % kTsBStages, s2 = (cb + 1) % kTsBStages;
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               tc_fence_after();
               if (leader) {
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);
-                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescNegateA, 1u);
+                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescA2, 1u);
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);
               }
             }
@@ -204,15 +212,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           if (leader) umma_commit(bars.acc_full(d_col / kMaxN, h));
           __syncwarp();
         }
+        if (G.wait_d_free) ++df;
         if (G.fresh_a) mca += nk;
         const bool becomes_a = (G.kind == kNodeChain || G.kind == kNodeChainAddU ||
                                 (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
         if (becomes_a) abuf ^= 1u;
       }
+  }
   } else {
+#if B200MD_TS_WARPGROUPS
+    ts_regs_acquire<kTsRegsEpilogue>();
+#endif
     // ===== epilogue warps =====
     const int q = warp & 3;
-    const int part = (warp - 2) >> 2;
+    const int part = (warp - kTsFirstEpiWarp) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base_all + ((uint32_t)(q * 32) << 16);
     const uint32_t sa_bias = s_base + L.bias;
@@ -301,12 +314,19 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         }
       } else {
         // aggregated messages (mean: / max(deg, 1)), reset for the next layer   models/egnn.py:178-183
+        // (the rows of chunk c + 1 are requested before chunk c is converted and published)
+        float ahead[kTsCols];
+#pragma unroll
+        for (int j = 0; j < kTsCols; ++j) ahead[j] = 0.f;
+        if (valid) load_cols(a.agg + node * M + part * kTsCols, ahead);
         for (int c = 0; c < M / 64; ++c) {
           const int col0 = c * 64 + part * kTsCols;
           float v[kTsCols];
           if (valid) {
             float* ap = a.agg + node * M + col0;
-            load_cols(ap, v);
+#pragma unroll
+            for (int j = 0; j < kTsCols; ++j) v[j] = ahead[j];
+            if (c + 1 < M / 64) load_cols(ap + 64, ahead);
             if (a.message_mean) {
 #pragma unroll
               for (int j = 0; j < kTsCols; ++j) v[j] = v[j] / degf;
@@ -340,6 +360,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         const bool becomes_a = (G.kind == kNodeChain || G.kind == kNodeChainAddU ||
                                 (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
         int waited = -1;
+        // the rows this epilogue adds to the accumulator (U, or the residual h) travel one chunk ahead of their use:
+        // the L2 / HBM round trip of chunk c + 1 is hidden behind the conversion of chunk c (and, for chunk 0,
+        // behind the wait for the accumulator)
+        const float* side_rows = nullptr;
+        if (valid && G.kind == kNodeChainAddU) side_rows = a.U + node * H;
+        if (valid && G.kind == kNodeChainLast && a.residual) side_rows = a.h + node * H;
+        float side[kTsCols];
+#pragma unroll
+        for (int j = 0; j < kTsCols; ++j) side[j] = 0.f;
+        if (side_rows) load_cols(side_rows + part * kTsCols, side);
         for (int c = 0; c < nchunks; ++c) {
           const int need = ts_last_group_of_chunk(c, nh);
           if (need > waited) {
@@ -351,6 +381,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           uint32_t r[kTsCols];
           float v[kTsCols];
           tmem_load_cols(lane_taddr + d_col + col0, r);
+          float u[kTsCols];
+#pragma unroll
+          for (int j = 0; j < kTsCols; ++j) u[j] = side[j];
+          if (side_rows && c + 1 < nchunks) load_cols(side_rows + col0 + 64, side);
           if (G.kind == kNodeChain) {
 #pragma unroll
             for (int j = 0; j < kTsCols / 4; ++j) {
@@ -359,13 +393,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               silu2(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
             }
           } else if (G.kind == kNodeChainAddU) {
-            float u[kTsCols];
-            if (valid) {
-              load_cols(a.U + node * H + col0, u);
-            } else {
-#pragma unroll
-              for (int j = 0; j < kTsCols; ++j) u[j] = 0.f;
-            }
 #pragma unroll
             for (int j = 0; j < kTsCols / 2; ++j)
               silu2(fma2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), unscale2, pack2(u[2 * j], u[2 * j + 1])), v[2 * j], v[2 * j + 1]);
@@ -381,10 +408,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             if (G.kind == kNodeChainLast) {
               if (valid) {
                 if (a.residual) {
-                  float old[kTsCols];
-                  load_cols(a.h + node * H + col0, old);
 #pragma unroll
-                  for (int j = 0; j < kTsCols; ++j) v[j] = old[j] + v[j];
+                  for (int j = 0; j < kTsCols; ++j) v[j] = u[j] + v[j];
                 }
                 store_cols(a.h + node * H + col0, v);
               }
@@ -411,13 +436,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             }
           }
           if (becomes_a) publish(d_col + (uint32_t)col0, v);
+          if (G.signal_d_free) {   // every column group that ends inside this chunk is drained now
+#pragma unroll
+            for (int h = 0; h < kTsNSplit; ++h)
+              if ((h + 1) * nh > c * 64 && (h + 1) * nh <= (c + 1) * 64) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars.d_free(h));
+              }
+          }
         }
         ++uses[dbuf];
-        if (G.signal_d_free) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars.d_free());
-        }
         if (becomes_a) abuf ^= 1u;
       }
 

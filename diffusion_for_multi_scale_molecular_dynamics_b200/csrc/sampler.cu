@@ -118,6 +118,22 @@ int enqueue_step(const StepContext& c, int i, const PcStepScalars* cur) {
   return B200MD_OK;
 }
 
+thread_local int g_last_mode = 0;   // 1: the last b200md_pc_sample of this thread replayed a graph, 0: direct launches
+
+// Stream capture is refused on the legacy default stream (which is what torch.cuda.current_stream() is unless the caller
+// changes it), so the step is always captured on a private non-blocking stream -- nothing executes during capture --
+// and the instantiated graph is launched on the caller's stream.  One capture stream per device, created on first use.
+cudaStream_t capture_stream() {
+  static cudaStream_t streams[PerDeviceOnce::kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= PerDeviceOnce::kMaxDevices) return nullptr;
+  if (streams[dev] == nullptr && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    streams[dev] = nullptr;
+  }
+  return streams[dev];
+}
+
 bool graph_mode_wanted() {
   if (g_profile_on) return false;   // per-class timing records events around every launch
   const char* env = getenv("B200MD_PC_DIRECT");
@@ -151,6 +167,7 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed, const b
   if (T < 2 || s->start_step_index > T || s->start_step_index <= s->end_step_index || s->start_step_index <= 0 ||
       s->end_step_index < 0 || s->number_of_corrector_steps < 0)
     return B200MD_ERR_INVALID_ARGUMENT;
+  g_last_mode = 0;
   if (B == 0) return B200MD_OK;
   EgnnLayout lay;
   int rc = build_layout(*cfg, lay);
@@ -174,7 +191,8 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed, const b
   const int n_steps = s->start_step_index - s->end_step_index;
   const int64_t state_offset = base + logits_bytes + score_bytes;
   const bool table_fits = n_steps <= B200MD_PC_MAX_GRAPH_STEPS && state_offset + pc_state_bytes(n_steps) <= workspace_bytes;
-  if (graph_mode_wanted() && table_fits && n_steps >= 2) {
+  cudaStream_t cap = (graph_mode_wanted() && table_fits && n_steps >= 2) ? capture_stream() : nullptr;
+  if (cap != nullptr) {
     PcDeviceState dev;
     dev.cursor = reinterpret_cast<int32_t*>(wbase + state_offset);
     dev.current = reinterpret_cast<PcStepScalars*>(wbase + state_offset + 128);
@@ -190,14 +208,16 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed, const b
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     const unsigned long long launches_before = g_launch_count;
-    e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+    e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
     if (e == cudaSuccess) {
+      c.st = cap;
       rc = enqueue_step(c, 0, dev.current);
+      c.st = st;
       if (rc == B200MD_OK) {
-        pc_advance_kernel<<<1, 1, 0, st>>>(dev.current, dev.table, dev.cursor, n_steps);
+        pc_advance_kernel<<<1, 1, 0, cap>>>(dev.current, dev.table, dev.cursor, n_steps);
         ++g_launch_count;
       }
-      e = cudaStreamEndCapture(st, &graph);   // always end the capture, also after an error inside it
+      e = cudaStreamEndCapture(cap, &graph);   // always end the capture, also after an error inside it
       if (rc != B200MD_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
       if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
       if (graph) cudaGraphDestroy(graph);
@@ -213,6 +233,7 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed, const b
       // an executable graph that is still in flight is freed asynchronously when its launches complete
       cudaGraphExecDestroy(exec);
       if (e != cudaSuccess) return set_cuda_error(e);
+      g_last_mode = 1;
       return B200MD_OK;
     }
     cudaGetLastError();   // capture or instantiation refused (e.g. the caller is itself capturing): direct launches
@@ -225,5 +246,7 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed, const b
   }
   return B200MD_OK;
 }
+
+int b200md_pc_sample_last_mode(void) { return g_last_mode; }
 
 }  // extern "C"

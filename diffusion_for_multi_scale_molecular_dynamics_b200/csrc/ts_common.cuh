@@ -14,7 +14,28 @@ constexpr int kTsSlots = 4;                       // K-chunk slots of the "A rea
 constexpr int kTsParts = 2;                       // epilogue warps per lane quarter
 constexpr int kTsCols = 64 / kTsParts;            // accumulator columns one epilogue thread converts per chunk
 constexpr int kTsEpiWarps = 4 * kTsParts;
-constexpr int kTsThreads = 32 * (2 + kTsEpiWarps);
+// Warp roles.  Default (B200MD_TS_WARPGROUPS = 0): 10 warps, 0 = weight producer, 1 = MMA issuer, 2-9 = epilogue; 168
+// registers per thread (a 320-thread block cannot be launched with more: the register file is handed out in units of
+// four warps, which is also why __maxnreg__(200) fails with "too many resources requested").
+// B200MD_TS_WARPGROUPS = 1 lays the roles out by WARPGROUP so that registers can be moved between them with setmaxnreg:
+//   warps 0-3  : 0 = weight producer, 1 = MMA issuer, 2-3 idle     -> shrink to kTsRegsControl registers per thread
+//   warps 4-11 : the 8 epilogue warps (two warpgroups)             -> grow to kTsRegsEpilogue
+// (384 threads are compiled for 168 registers; the control group gives back (168 - 56) x 128 registers and each epilogue
+// group takes (224 - 168) x 128; the setmaxnreg must sit at the top of each group's branch, ptxas budgets the code it
+// dominates.)  Measured on one box, 4096 x 64 atoms: edge launch 18.8 ms (default) vs 19.2 ms (warpgroups) vs 19.5 ms
+// (warpgroups + the next tile's P / Q rows requested one chunk ahead, B200MD_TS_PQ_AHEAD): with 227 KB of shared memory
+// there is almost no L1 left, and 64 KB of gathers in flight per SM thrash it -- more registers do not buy deeper
+// prefetch here.  Kept as a compile-time option.
+#ifndef B200MD_TS_WARPGROUPS
+#define B200MD_TS_WARPGROUPS 0
+#endif
+constexpr int kTsFirstEpiWarp = B200MD_TS_WARPGROUPS ? 4 : 2;
+constexpr int kTsThreads = 32 * (kTsFirstEpiWarp + kTsEpiWarps);
+constexpr int kTsRegsControl = 56, kTsRegsEpilogue = 224;
+template <int N>
+__device__ __forceinline__ void ts_regs_release() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void ts_regs_acquire() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // Index of the last column group (of `nh` columns each) that accumulator chunk c (columns [64 c, 64 c + 64)) reads.
 // Compares instead of (64 c + 64 + nh - 1) / nh - 1: an integer division is an I2F / MUFU.RCP / F2I chain on the SFU
@@ -81,6 +102,8 @@ __device__ __forceinline__ uint32_t pack_f16x2_inf(float lo_elem, float hi_elem)
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
+constexpr uint32_t kIdescNegateA = 1u << 13;
+constexpr uint32_t kIdescA2 = kIdescNegateA | kIdescAFormatBf16;   // A_2 is stored negated, in BF16 (tc_common.cuh)
 // kTsCols activations -> per K step (16 values) [hi x 8 | -lo x 8] packed fp16 pairs: the A-operand image of those
 // columns.  hi = fp16(x); the second part holds fp16(hi - x) = -lo, one mixed-precision subtract per element
 // (sub.f32.f16, SASS FHADD) instead of an unpack and a subtract; the A_2 B_1 MMA negates it back (a_negate bit of the
@@ -102,11 +125,9 @@ __device__ __forceinline__ void split_hi_lo(const float (&v)[kTsCols], uint32_t 
           : "=f"(n0), "=f"(n1)
           : "r"(hi), "f"(x0), "f"(x1));
       w[16 * s + i] = hi;
-      w[16 * s + 8 + i] = pack_f16x2_inf(n0, n1);
+      w[16 * s + 8 + i] = pack_lo_x2(n0, n1);
     }
 }
-constexpr uint32_t kIdescNegateA = 1u << 13;
-
 // Packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes per instruction) for the bias add and the SiLU arithmetic.
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
   uint64_t r;

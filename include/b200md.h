@@ -411,6 +411,8 @@ int b200md_pc_sample(const b200md_egnn_config* cfg, const float* packed,
                      const float* lattice, int64_t n_samples, int32_t n_atoms, uint64_t seed,
                      uint64_t sample_offset, void* workspace, int64_t workspace_bytes,
                      int64_t edge_capacity, int32_t* status, int32_t impl, b200md_stream_t stream);
+/* 1 if the last b200md_pc_sample call of this thread replayed the captured step graph, 0 if it launched directly */
+int b200md_pc_sample_last_mode(void);
 /* whole workspace of b200md_pc_sample: b200md_egnn_workspace_bytes + logits + scores + the device-side step table */
 int64_t b200md_pc_sample_workspace_bytes(const b200md_egnn_config* cfg, int64_t n_samples,
                                          int32_t n_atoms, int64_t edge_capacity);

@@ -82,13 +82,16 @@ def test_graph_replay_equals_direct_launches(cuda_device, n_corr, start, end, mo
     a0 = torch.full((B, N), 2)
     make = lambda: AXL(A=a0.clone().to(cuda_device), X=x0.clone().to(cuda_device), L=lattice.to(cuda_device))  # noqa: E731
     from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+    gen.axl_network.packed_weights(cuda_device)   # the packing kernels are launched (and counted) on first use
     before = _cabi.launch_count()
     replayed = gen.sample_from_noisy_composition(make(), start, end)
     launches_graph = _cabi.launch_count() - before
+    assert _cabi.lib().b200md_pc_sample_last_mode() == 1, "the step graph was not captured / instantiated"
     monkeypatch.setenv("B200MD_PC_DIRECT", "1")
     before = _cabi.launch_count()
     direct = gen.sample_from_noisy_composition(make(), start, end)
     launches_direct = _cabi.launch_count() - before
+    assert _cabi.lib().b200md_pc_sample_last_mode() == 0
     assert torch.equal(replayed.A, direct.A)
     assert torus_distance(replayed.X, direct.X).max() < 2e-5
     assert not torch.equal(replayed.X.cpu(), x0)
