@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 
   for (int t = threadIdx.x; t < p.n_gemms * kMaxN; t += kTsThreads) {
     const int g = t / kMaxN, n = t - g * kMaxN;
-    s_bias[t] = (n < p.gN[g] && p.gB[g] >= 0) ? p.packed[p.gB[g] + n] : 0.f;
+    s_bias[t] = (n < p.gN[g] && p.gB[g] >= 0) ? p.packed[p.gB[g] + n] * kF16ActScale : 0.f;   // x kF16ActScale: ts_common.cuh
   }
   for (int t = threadIdx.x; t < kMaxN; t += kTsThreads) {
     s_wr[t] = (t < M) ? p.packed[a.msg_wr + t] : 0.f;
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         const int r = __ffs(m) - 1;
         const float sum = lds32(seg_read + (uint32_t)r * (kTsCols * 4) + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4));
         const int s = __shfl_sync(0xffffffffu, ed.src, r);
-        red_add_f32(column + (int64_t)s * ld, sum);
+        red_add_f32(column + (int64_t)s * ld, sum * (1.0f / kF16ActScale));   // v is kF16ActScale x the message
       }
       __syncwarp();
     };
@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       }
       if (ed.is_tail && ed.valid) {
 #pragma unroll
-        for (int j = 0; j < kTsCols / 4; ++j) red_add_v4(target_row + 4 * j, sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+        for (int j = 0; j < kTsCols / 4; ++j)
+          red_add_v4(target_row + 4 * j, sum[4 * j] * (1.0f / kF16ActScale), sum[4 * j + 1] * (1.0f / kF16ActScale),
+                     sum[4 * j + 2] * (1.0f / kF16ActScale), sum[4 * j + 3] * (1.0f / kF16ActScale));
       }
     };
 #endif
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     struct PQ {
       float4 p[kTsCols / 4], q[kTsCols / 4];
     };
+    const uint64_t act2 = pack2(kF16ActScale, kF16ActScale);   // the first activation is scaled like every other A operand
     auto load_pq = [&](const Edge& ed, int c, PQ& t) {
       if (ed.valid) {
         const int col0 = c * 64 + part * kTsCols;
@@ -419,8 +422,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #pragma unroll
         for (int j = 0; j < kTsCols / 4; ++j) {
           const float4 pv = t.p[j], qv = t.q[j], wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
-          silu2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), v[4 * j + 0], v[4 * j + 1]);
-          silu2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), v[4 * j + 2], v[4 * j + 3]);
+          silu2(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), v[4 * j + 0], v[4 * j + 1]);
+          silu2(mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2), v[4 * j + 2], v[4 * j + 3]);
         }
       } else {
 #pragma unroll
@@ -442,8 +445,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         for (int j = 0; j < kTsCols / 4; ++j) {
           const float4 pv = __ldg(p4 + j), qv = __ldg(q4 + j), wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
           // silu((P + Q) + radial * w_r), two columns per instruction
-          silu2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), v[4 * j + 0], v[4 * j + 1]);
-          silu2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), v[4 * j + 2], v[4 * j + 3]);
+          silu2(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), v[4 * j + 0], v[4 * j + 1]);
+          silu2(mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2), v[4 * j + 2], v[4 * j + 3]);
         }
       } else {
 #pragma unroll
@@ -481,7 +484,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         const uint32_t d_col = (gc & 1u) * kMaxN;
         const int nchunks = p.gN[g] / 64, nh = p.gN[g] / kTsEdgeNSplit;
         const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
-        const float unscale = lds32(pipe.s_base + L.scale + (uint32_t)g * 4u);   // accumulator = 2^s x product
+        // accumulator = 2^s (weights) x kF16ActScale (A operand) x product; kF16ActScale x pre-activation = acc 2^-s + bias'
+        const float unscale = lds32(pipe.s_base + L.scale + (uint32_t)g * 4u);
         const uint64_t unscale2 = pack2(unscale, unscale);
         if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
           next = load_edge(it + 1);
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             TS_TRACE(2, g * 16 + c);
           }
         };
-        // v = silu(accumulator * 2^-s + bias)
+        // v = kF16ActScale x silu(pre-activation), with bias' = kF16ActScale x bias in shared memory
         auto activate = [&](const uint32_t (&r)[kTsCols], int col0, float (&v)[kTsCols]) {
           TS_TRACE(4, col0);
 #if B200MD_TS_SFU_TOKEN
@@ -625,6 +629,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         float phi = 0.f;
 #pragma unroll
         for (int j = 0; j < kTsParts; ++j) phi += dot_slot[j * kTileM + row];
+        phi *= 1.0f / kF16ActScale;   // the last hidden activation was kF16ActScale x the true one (exact)
         if (a.tanh_out) phi = tanhf(phi);
         float norm = 1.0f;
         if (a.normalize) norm = tanhf(cur.radial) / sqrtf(cur.radial + 1e-16f);  // models/egnn.py:240-264, epsilon = 1e-8

@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 
   for (int t = threadIdx.x; t < a.n_gemms * kMaxN; t += kTsThreads) {
     const int g = t / kMaxN, n = t - g * kMaxN;
-    s_bias[t] = (n < a.g[g].N && a.g[g].bias >= 0) ? Wp[a.g[g].bias + n] : 0.f;
+    // the bias of a SiLU layer is stored x kF16ActScale, like the activation it produces (ts_common.cuh)
+    s_bias[t] = (n < a.g[g].N && a.g[g].bias >= 0) ? Wp[a.g[g].bias + n] * (a.g[g].kind == kNodeChain ? kF16ActScale : 1.0f) : 0.f;
   }
   if (threadIdx.x < a.n_gemms) reinterpret_cast<float*>(smem + L.scale)[threadIdx.x] = a.wtc[a.g[threadIdx.x].unscale];
   float* s_readout = reinterpret_cast<float*>(smem + L.readout);
@@ -234,7 +235,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     unsigned local_status = 0;
     float checksum = 0.f;   // inf / NaN of an fp16 overflow propagates into everything stored: one test at the end
 
-    auto publish = [&](uint32_t col, const float (&v)[kTsCols]) {
+    // `scale`: kF16ActScale for values that are not scaled yet (every A operand is stored x kF16ActScale), 1 for the
+    // outputs of the SiLU layers, which already are
+    auto publish = [&](uint32_t col, const float (&v_in)[kTsCols], float scale) {
+      float v[kTsCols];
+#pragma unroll
+      for (int j = 0; j < kTsCols; ++j) v[j] = v_in[j] * scale;
       uint32_t w[kTsCols];
       split_hi_lo(v, w);
 #pragma unroll
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             v[j] = valid ? Wp[a.embed_b + o] + (Wp[a.embed_w + o * a.F0] * sg + Wp[a.embed_w + o * a.F0 + 1 + atc]) : 0.f;
           }
           if (valid) store_cols(a.h + node * H + col0, v);
-          publish(a_col0 + (uint32_t)col0, v);
+          publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
         }
         if (valid) {
           float zero[kTsCols];
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 #pragma unroll
             for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
           }
-          publish(a_col0 + (uint32_t)col0, v);
+          publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
         }
       }
 
@@ -355,7 +361,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         const uint32_t d_col = dbuf * kMaxN;
         const int nchunks = G.N / 64, nh = G.N / kTsNSplit;
         const uint32_t bias = sa_bias + (uint32_t)(g * kMaxN) * 4u;
-        const float unscale = lds32(s_base + L.scale + (uint32_t)g * 4u);   // accumulator = 2^s x product
+        // accumulator = 2^s (weights) x kF16ActScale (A operand) x product
+        const float unscale = lds32(s_base + L.scale + (uint32_t)g * 4u);   // 2^-s: gives kF16ActScale x the product
+        const float unscale_true = unscale * (1.0f / kF16ActScale);         // gives the product itself
         const uint64_t unscale2 = pack2(unscale, unscale);
         const bool becomes_a = (G.kind == kNodeChain || G.kind == kNodeChainAddU ||
                                 (G.kind == kNodeChainLast && g + 1 < a.n_gemms));
@@ -395,15 +403,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           } else if (G.kind == kNodeChainAddU) {
 #pragma unroll
             for (int j = 0; j < kTsCols / 2; ++j)
-              silu2(fma2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), unscale2, pack2(u[2 * j], u[2 * j + 1])), v[2 * j], v[2 * j + 1]);
+              silu2(fma2(pack2(u[2 * j], u[2 * j + 1]), pack2(kF16ActScale, kF16ActScale),
+                         mul2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), unscale2)), v[2 * j], v[2 * j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < kTsCols / 4; ++j) {
               const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), unscale, b.x);
-              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), unscale, b.y);
-              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), unscale, b.z);
-              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), unscale, b.w);
+              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), unscale_true, b.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), unscale_true, b.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), unscale_true, b.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), unscale_true, b.w);
             }
             if (G.kind == kNodeChainLast) {
               if (valid) {
@@ -435,7 +444,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               for (int j = 0; j < kTsCols; ++j) checksum += v[j];
             }
           }
-          if (becomes_a) publish(d_col + (uint32_t)col0, v);
+          if (becomes_a) publish(d_col + (uint32_t)col0, v, G.kind == kNodeChainLast ? kF16ActScale : 1.0f);
           if (G.signal_d_free) {   // every column group that ends inside this chunk is drained now
 #pragma unroll
             for (int h = 0; h < kTsNSplit; ++h)

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_edge_tc_kernel(const EdgeTcA
     s_wlast[t] = (t < p.gN[p.n_gemms - 1]) ? p.packed[a.coord_last_w + t] : 0.f;
   }
   if (threadIdx.x < p.n_gemms)
-    s_scale[threadIdx.x] = (PREC == kF16x3) ? p.wtc[p.gW[threadIdx.x] + weight_unscale_offset(p.gK[threadIdx.x], p.gN[threadIdx.x])] : 1.0f;
+    s_scale[threadIdx.x] = (PREC == kF16x3) ? p.wtc[p.gW[threadIdx.x] + weight_unscale_offset(p.gK[threadIdx.x], p.gN[threadIdx.x])] * (1.0f / kF16ActScale) : 1.0f;   // A operands are stored x kF16ActScale
   Pipe<PREC> pipe;
   pipe.setup(smem);
   const TileSchedule sched = make_schedule(n_tiles);

@@ -150,13 +150,17 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
+// The TS kernels keep every activation multiplied by kF16ActScale (tc_common.cuh): `x` below is kF16ActScale times the
+// pre-activation and the result kF16ActScale times its SiLU -- the factor rides on the multiplier and the bias of the
+// FMA that produces x and on the exp2 constant, so it costs no instruction.
+constexpr float kTsExpConst = -1.4426950408889634f / kF16ActScale;
 // (silu(x0), silu(x1)) of a packed pair: x / (1 + 2^(-x log2 e)) with the SFU exp2 / reciprocal (about 2 ulp each, far
 // below the 1e-5 parity bound).  Moving the reciprocal to three Newton steps on the FMA pipe halves the SFU load and
 // saves 2.6 % of the cycles, but the extra FMA work lowers the clock the 1000 W power cap allows (1657 -> 1605 MHz):
 // +-1 % on the launch, within noise, so the SFU version stays.
 __device__ __forceinline__ void silu2(uint64_t x, float& o0, float& o1) {
   float t0, t1, e0, e1, r0, r1;
-  unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+  unpack2(mul2(x, pack2(kTsExpConst, kTsExpConst)), t0, t1);
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
   unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), t0, t1);
@@ -168,7 +172,7 @@ __device__ __forceinline__ void silu2(uint64_t x, float& o0, float& o1) {
 // be scheduled before the last SFU result exists.
 __device__ __forceinline__ void silu2_dep(uint64_t x, float& o0, float& o1, uint32_t& dep) {
   float t0, t1, e0, e1, r0, r1;
-  unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+  unpack2(mul2(x, pack2(kTsExpConst, kTsExpConst)), t0, t1);
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
   unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), t0, t1);
