@@ -27,6 +27,7 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
   float* lat = pz + N;  // [27][3]
   __shared__ float s_cell[9];
   __shared__ unsigned long long s_total;
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   stage_structure(positions + b * N * 3, cell + b * 9, relative, N, px, py, pz, lat, s_cell);
   if (threadIdx.x == 0) {
@@ -34,16 +35,18 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
     if (!(shortest_cell_crossing_distance(s_cell) > rc)) atomicOr(status, (int)B200MD_STATUS_CUTOFF_TOO_LARGE);
   }
   __syncthreads();
+  image_cull_setup(&s_cull, px, py, pz, N, s_cell);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   unsigned long long local = 0;
   if (mode == B200MD_GRAPH_UNIQUE_PAIRS) {
     for (int i = warp; i < N; i += nwarps) {
       const float xi = px[i], yi = py[i], zi = pz[i];
+      const unsigned candidates = image_candidates(&s_cull, xi, yi, zi, rc);
       int deg = 0;
       for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;
         bool hit = false;
-        if (j < N) hit = any_image_hit(xi, yi, zi, px[j], py[j], pz[j], lat, rc2);
+        if (j < N) hit = first_image_hit_among(xi, yi, zi, px[j], py[j], pz[j], lat, rc2, candidates) >= 0;
         deg += __popc(__ballot_sync(0xffffffffu, hit));
       }
       if (lane == 0) { counts[b * N + i] = deg; local += deg; }
@@ -54,6 +57,10 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
       const float xi = px[i], yi = py[i], zi = pz[i];
       const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
       int deg = 0;
+      if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) {   // no atom of this image can be inside the cutoff
+        if (lane == 0) counts[(b * 27 + img) * N + i] = 0;
+        continue;
+      }
       for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;
         bool hit = false;
@@ -70,7 +77,7 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
 }
 
 __global__ void radius_graph_fill_kernel(const float* __restrict__ positions, const float* __restrict__ cell,
-                                         int relative, float rc2, int32_t N, int32_t mode,
+                                         int relative, float rc, float rc2, int32_t N, int32_t mode,
                                          const int64_t* __restrict__ offsets, int64_t node_offset,
                                          int64_t* __restrict__ src_out, int64_t* __restrict__ dst_out,
                                          float* __restrict__ shifts_out, int64_t* __restrict__ edge_batch) {
@@ -79,9 +86,11 @@ __global__ void radius_graph_fill_kernel(const float* __restrict__ positions, co
   float* lat = pz + N;  // [27][3]
   float* scratch = lat + 81;  // per-warp [N] d2 + [N] j  (PER_IMAGE mode only)
   __shared__ float s_cell[9];
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   stage_structure(positions + b * N * 3, cell + b * 9, relative, N, px, py, pz, lat, s_cell);
   __syncthreads();
+  image_cull_setup(&s_cull, px, py, pz, N, s_cell);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int64_t base_node = b * node_offset;
@@ -89,10 +98,11 @@ __global__ void radius_graph_fill_kernel(const float* __restrict__ positions, co
     for (int i = warp; i < N; i += nwarps) {
       const float xi = px[i], yi = py[i], zi = pz[i];
       int64_t pos = offsets[b * N + i];
+      const unsigned candidates = image_candidates(&s_cull, xi, yi, zi, rc);
       for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;
         int img = -1;
-        if (j < N) img = first_image_hit(xi, yi, zi, px[j], py[j], pz[j], lat, rc2);
+        if (j < N) img = first_image_hit_among(xi, yi, zi, px[j], py[j], pz[j], lat, rc2, candidates);
         const unsigned ballot = __ballot_sync(0xffffffffu, img >= 0);
         if (img >= 0) {
           const int64_t e = pos + __popc(ballot & lt_mask);
@@ -112,6 +122,7 @@ __global__ void radius_graph_fill_kernel(const float* __restrict__ positions, co
       const float xi = px[i], yi = py[i], zi = pz[i];
       const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
       int cnt = 0;
+      if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) continue;   // an empty row (its count is 0)
       for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;
         bool hit = false;
@@ -154,6 +165,7 @@ __global__ void egnn_graph_count_kernel(const float* __restrict__ x_rel, const f
   float* lat = pz + N;
   __shared__ float s_cell[9];
   __shared__ int s_total;
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   if (threadIdx.x == 0) s_total = 0;
   if (!fully_connected) {
@@ -174,9 +186,11 @@ __global__ void egnn_graph_count_kernel(const float* __restrict__ x_rel, const f
   // EGNN box guarantees unless the cutoff assert above has fired
   const float Lx = s_cell[0], Ly = s_cell[4], Lz = s_cell[8];
   const bool min_image = !fully_connected && (2.0f * rc < fminf(Lx, fminf(Ly, Lz)));
+  if (!fully_connected && !min_image) image_cull_setup(&s_cull, px, py, pz, N, s_cell);   // CTA-uniform branch
   for (int i = warp; i < N; i += nwarps) {
     float xi = 0.f, yi = 0.f, zi = 0.f;
     if (!fully_connected) { xi = px[i]; yi = py[i]; zi = pz[i]; }
+    const unsigned candidates = (!fully_connected && !min_image) ? image_candidates(&s_cull, xi, yi, zi, rc) : 0u;
     int d = 0;
     for (int w = 0; w < W; ++w) {
       const int j = w * 32 + lane;
@@ -184,7 +198,7 @@ __global__ void egnn_graph_count_kernel(const float* __restrict__ x_rel, const f
       if (j < N)
         hit = fully_connected ? (j != i)
                               : (min_image ? min_image_hit(xi, yi, zi, px[j], py[j], pz[j], Lx, Ly, Lz, rc2)
-                                           : any_image_hit(xi, yi, zi, px[j], py[j], pz[j], lat, rc2));
+                                           : first_image_hit_among(xi, yi, zi, px[j], py[j], pz[j], lat, rc2, candidates) >= 0);
       const unsigned ballot = __ballot_sync(0xffffffffu, hit);
       if (lane == 0) bitmask[(b * N + i) * W + w] = ballot;
       d += __popc(ballot);
@@ -368,7 +382,7 @@ int b200md_radius_graph_fill(const float* positions, const float* cell, int32_t 
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(radius_graph_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); radius_graph_fill_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
-      positions, cell, positions_are_relative, radial_cutoff * radial_cutoff, n_atoms, mode, offsets,
+      positions, cell, positions_are_relative, radial_cutoff, radial_cutoff * radial_cutoff, n_atoms, mode, offsets,
       node_index_offset, src_out, dst_out, shifts_out, edge_batch); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;

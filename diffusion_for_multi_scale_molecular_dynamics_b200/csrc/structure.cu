@@ -26,10 +26,12 @@ __global__ void pair_distances_count_kernel(const float* __restrict__ positions,
   float* lat = pz + N;  // [27][3]
   __shared__ float s_cell[9];
   __shared__ unsigned long long s_total;
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   stage_structure(positions + b * N * 3, cell + b * 9, relative, N, px, py, pz, lat, s_cell);
   if (threadIdx.x == 0) s_total = 0ull;
   __syncthreads();
+  image_cull_setup(&s_cull, px, py, pz, N, s_cell);   // graph.cuh: rows (image, atom) that cannot reach the cutoff are skipped
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   unsigned long long local = 0;
   for (int r = warp; r < 27 * N; r += nwarps) {
@@ -37,6 +39,10 @@ __global__ void pair_distances_count_kernel(const float* __restrict__ positions,
     const float xi = px[i], yi = py[i], zi = pz[i];
     const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
     int n = 0;
+    if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) {
+      if (lane == 0) counts[(b * 27 + img) * N + i] = 0;
+      continue;
+    }
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int j = j0 + lane;
       bool hit = false;
@@ -59,9 +65,11 @@ __global__ void pair_distances_fill_kernel(const float* __restrict__ positions, 
   float* lat = pz + N;          // [27][3]
   float* scratch = lat + 81;    // per-warp [N] d2, [N] d, [N] j
   __shared__ float s_cell[9];
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   stage_structure(positions + b * N * 3, cell + b * 9, relative, N, px, py, pz, lat, s_cell);
   __syncthreads();
+  image_cull_setup(&s_cull, px, py, pz, N, s_cell);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   float* wd2 = scratch + (size_t)warp * 3 * N;
@@ -72,6 +80,7 @@ __global__ void pair_distances_fill_kernel(const float* __restrict__ positions, 
     const float xi = px[i], yi = py[i], zi = pz[i];
     const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
     int cnt = 0;
+    if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) continue;   // an empty row
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int j = j0 + lane;
       bool hit = false;
@@ -112,6 +121,7 @@ __global__ void repulsive_pseudo_force_kernel(const float* __restrict__ x_rel, c
   float* px = smem; float* py = px + N; float* pz = py + N;
   float* lat = pz + N;  // [27][3]
   __shared__ float s_cell[9];
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   if (threadIdx.x < 9) {
     const int r = threadIdx.x / 3, c = threadIdx.x % 3;
@@ -122,11 +132,13 @@ __global__ void repulsive_pseudo_force_kernel(const float* __restrict__ x_rel, c
   if (threadIdx.x == 0 && !(shortest_cell_crossing_distance(s_cell) > rc))
     atomicOr(status, (int)B200MD_STATUS_CUTOFF_TOO_LARGE);
   __syncthreads();
+  image_cull_setup(&s_cull, px, py, pz, N, s_cell);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int i = warp; i < N; i += nwarps) {
     const float xi = px[i], yi = py[i], zi = pz[i];
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    for (int img = 0; img < 27; ++img) {
+    for (unsigned m = image_candidates(&s_cull, xi, yi, zi, rc); m != 0; m &= m - 1) {   // images in ascending order
+      const int img = __ffs(m) - 1;
       const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
       for (int j = lane; j < N; j += 32) {
         float d2;
@@ -179,6 +191,7 @@ __global__ void stillinger_weber_energy_kernel(const float* __restrict__ x_rel, 
   __shared__ float s_cell[9];
   __shared__ double s_energy;
   __shared__ int s_skip;
+  __shared__ ImageCull s_cull;
   const int64_t b = blockIdx.x;
   if (threadIdx.x < 9) {
     const int r = threadIdx.x / 3, c = threadIdx.x % 3;
@@ -201,6 +214,7 @@ __global__ void stillinger_weber_energy_kernel(const float* __restrict__ x_rel, 
   if (bad_type) atomicOr(status, (int)B200MD_STATUS_A_OUT_OF_RANGE);
   __syncthreads();
   if (s_skip) { if (threadIdx.x == 0) energies[b] = 0.0f; return; }
+  image_cull_setup(&s_cull, px, py, pz, N, s_cell);
   const SwEntry* table = reinterpret_cast<const SwEntry*>(params);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -212,7 +226,8 @@ __global__ void stillinger_weber_energy_kernel(const float* __restrict__ x_rel, 
     const float xi = px[i], yi = py[i], zi = pz[i];
     const int ti = types[i];
     int cnt = 0;
-    for (int img = 0; img < 27; ++img) {
+    for (unsigned m = image_candidates(&s_cull, xi, yi, zi, max_cut); m != 0; m &= m - 1) {   // images in ascending order
+      const int img = __ffs(m) - 1;
       const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
       for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;

@@ -305,7 +305,10 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
 // (Tried first: A_2 in BF16 -- fp32 exponent, 8 significant bits, no cliff at all -- with A_1 / B in FP16.  The
 // instruction descriptor has separate a_format / b_format fields, but kind::f16 with a_format != b_format raises
 // "illegal instruction" on B200; B200MD_F16X3_LO_BF16 = 1 keeps the experiment compilable.)
-constexpr float kF16ActScale = 4.0f;
+#ifndef B200MD_F16_ACT_SCALE
+#define B200MD_F16_ACT_SCALE 4.0f
+#endif
+constexpr float kF16ActScale = B200MD_F16_ACT_SCALE;   // a power of two (1.0f = no scaling, for A/B builds)
 #ifndef B200MD_F16X3_LO_BF16
 #define B200MD_F16X3_LO_BF16 0
 #endif

@@ -94,9 +94,28 @@ for B, N, length, rc in ((8192, 64, 16.5, 7.5), (1024, 512, 21.72, 7.5)):
     ms = timed(lambda: get_edges_with_radial_cutoff(rel, cell, rc), repeats=5)
     E = edges.shape[0]
     report(f"radius graph count + scan + fill (get_edges_with_radial_cutoff), N = {N}", ms, B * (12 * N + 36) + 16 * E,
-           f"{B} structures, {E / B:.0f} edges/structure; compute-bound sweep of N^2 x 27 image tests, includes the "
-           "host-side cumsum and one .item()")
+           f"{B} structures, {E / B:.0f} edges/structure; FP32-issue-bound sweep of N^2 pairs x the images that survive "
+           "the culling, includes the host-side cumsum and one .item()")
+# ---- general periodic adjacency (per-image edges, shifts): the Stillinger-Weber cutoff in the 4x4x4 supercell --------------
+from diffusion_for_multi_scale_molecular_dynamics_b200.utils.neighbors import get_periodic_adjacency_information  # noqa: E402
+for B, N, length, rc in ((1024, 512, 21.72, 3.77), (8192, 64, 10.86, 3.77)):
+    cart = torch.rand(B, N, 3, device=dev) * length
+    cell = torch.diag_embed(torch.full((B, 3), length, device=dev))
+    info = get_periodic_adjacency_information(cart, cell, rc)
+    ms = timed(lambda: get_periodic_adjacency_information(cart, cell, rc), repeats=5)
+    E = info.adjacency_matrix.shape[1]
+    report(f"periodic adjacency count + fill (get_periodic_adjacency_information), N = {N}, rc = {rc}", ms,
+           B * (12 * N + 36) + 36 * E, f"{B} structures, {E / B:.0f} per-image edges/structure (int64 pairs + shifts + batch "
+           f"index); L / rc = {length / rc:.1f}: image culling leaves (1 + 2 rc / L)^3 = {(1 + 2 * rc / length) ** 3:.1f} of 27 "
+           "images per atom; includes the host-side cumsum and one .item()")
 # ---- pair distances ----------------------------------------------------------------------------------------------------
+B, N, length = 1024, 512, 21.72
+cart = torch.rand(B, N, 3, device=dev) * length
+cell = torch.diag_embed(torch.full((B, 3), length, device=dev))
+d = compute_distances_in_batch(cart, cell, 5.0)
+ms = timed(lambda: compute_distances_in_batch(cart, cell, 5.0), repeats=5)
+report("pair_distances count + fill (compute_distances_in_batch), N = 512", ms, B * (12 * N + 36) + 4 * d.numel(),
+       f"{B} x {N} atoms, {d.numel() / B:.0f} distances/structure")
 B, N, length = 8192, 64, 10.86
 cart = torch.rand(B, N, 3, device=dev) * length
 cell = torch.diag_embed(torch.full((B, 3), length, device=dev))

@@ -46,12 +46,18 @@ def launches(tag: str) -> str:
 
 
 def full(tag: str) -> str:
-    raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}.ncu-rep", "--page", "raw", "--csv"],
+    import glob
+    reports = sorted(glob.glob(f"gpurun_out/prof_{tag}*.ncu-rep"))
+    return "".join(full_one(tag, report) for report in reports)
+
+
+def full_one(tag: str, report: str) -> str:
+    raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     header, units = rows[0], rows[1]
     index = {h: i for i, h in enumerate(header)}
-    out = [f"# ncu --set full ({tag}), one block per captured launch"]
+    out = [f"# ncu --set full ({tag}, {report.split('/')[-1]}), one block per captured launch"]
     for row in rows[2:]:
         out.append(f"kernel: {row[index['Kernel Name']]}")
         for metric in METRICS:
