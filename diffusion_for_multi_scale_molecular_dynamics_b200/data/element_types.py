@@ -1,4 +1,9 @@
-"""Element <-> integer index bookkeeping (reference: data/element_types.py:7-90)."""
+"""Chemical element names <-> integer atom-type indices (API mirror of the reference's data/element_types.py:7-90).
+
+The sampling path only needs the mapping in two places: ``SamplingConstraint`` (element names of the constrained
+atoms) and the Stillinger-Weber oracle (column order of the ``.sw`` file).  The contract that matters is the ORDER:
+atom type k is the k-th element name in alphabetical order, and the padding element maps to -1.
+"""
 from typing import Dict, List
 
 NULL_ELEMENT = "NULL_ELEMENT_FOR_PADDING"
@@ -6,19 +11,22 @@ NULL_ELEMENT_ID = -1
 
 
 class ElementTypes:
-    """Sorted element names and their indices; the index of an element is its rank in alphabetical order."""
+    """Alphabetically ranked element names: ``get_element_id("Ge") == 0`` and ``get_element_id("Si") == 1`` for SiGe."""
 
     def __init__(self, elements: List[str]):
         self.validate_elements(elements)
-        self._elements = sorted(elements)
-        self._ids = list(range(len(self._elements)))
-        self._element_to_id_map: Dict[str, int] = dict(zip(self._elements, self._ids))
-        self._id_to_element_map: Dict[int, str] = dict(zip(self._ids, self._elements))
+        ranked = sorted(elements)
+        self._elements = ranked
+        self._ids = list(range(len(ranked)))
+        self._element_to_id_map: Dict[str, int] = {name: rank for rank, name in enumerate(ranked)}
+        self._id_to_element_map: Dict[int, str] = {rank: name for rank, name in enumerate(ranked)}
+        # the padding element is addressable both ways, like in the reference
         self._element_to_id_map[NULL_ELEMENT] = NULL_ELEMENT_ID
         self._id_to_element_map[NULL_ELEMENT_ID] = NULL_ELEMENT
 
     @staticmethod
     def validate_elements(elements: List[str]):
+        """Reserved name and duplicates are refused with the reference's assertion messages."""
         assert NULL_ELEMENT not in elements, f"The element '{NULL_ELEMENT}' is reserved and should not be used."
         assert len(set(elements)) == len(elements), "Each entry in the elements list should be unique."
 

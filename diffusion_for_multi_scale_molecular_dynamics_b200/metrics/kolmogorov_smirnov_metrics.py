@@ -11,48 +11,39 @@ import torch
 
 
 class KolmogorovSmirnovMetrics:
-    """Kolmogorov Smirnov metrics."""
+    """Accumulates two families of scalar samples and compares their distributions (reference class of the same name)."""
 
     def __init__(self, maximum_number_of_samples: int = 1_000_000):
-        """Init method.
-
-        Args:
-            maximum_number_of_samples : maximum number of samples that will be aggregated. This is to avoid
-                memory use explosion.
-        """
+        """``maximum_number_of_samples`` caps each family: once a family holds that many values, further registrations
+        for it are dropped (a whole registration is kept or dropped, so the cap can be exceeded by one batch)."""
         self._reference_samples: List[torch.Tensor] = []
         self._predicted_samples: List[torch.Tensor] = []
         self.maximum_count = maximum_number_of_samples
         self.reference_count = 0
         self.predicted_count = 0
 
+    def _register(self, store: List[torch.Tensor], count: int, samples) -> int:
+        if count >= self.maximum_count:
+            return count
+        store.append(torch.as_tensor(samples).detach().flatten())
+        return count + len(samples)
+
     def register_reference_samples(self, reference_samples):
-        """Register reference samples."""
-        if self.reference_count < self.maximum_count:
-            self.reference_count += len(reference_samples)
-            self._reference_samples.append(torch.as_tensor(reference_samples).detach().flatten())
+        """Samples of the data distribution (e.g. pair distances or energies of the validation set)."""
+        self.reference_count = self._register(self._reference_samples, self.reference_count, reference_samples)
 
     def register_predicted_samples(self, predicted_samples):
-        """Register predicted samples."""
-        if self.predicted_count < self.maximum_count:
-            self.predicted_count += len(predicted_samples)
-            self._predicted_samples.append(torch.as_tensor(predicted_samples).detach().flatten())
+        """Samples of the generated structures."""
+        self.predicted_count = self._register(self._predicted_samples, self.predicted_count, predicted_samples)
 
     def reset(self):
-        """reset."""
-        self._reference_samples = []
-        self._predicted_samples = []
-        self.reference_count = 0
-        self.predicted_count = 0
+        """Forget everything registered so far."""
+        self._reference_samples, self._predicted_samples = [], []
+        self.reference_count = self.predicted_count = 0
 
     def compute_kolmogorov_smirnov_distance_and_pvalue(self) -> Tuple[float, float]:
-        """Two-sample, two-sided KS test between the predicted and the reference samples.
-
-        Returns:
-            ks_distance, p_value: the Kolmogorov-Smirnov test statistic (a "distance")
-                and the statistical test's p-value.
-        """
-        reference_samples = torch.cat(self._reference_samples).cpu().numpy()
-        predicted_samples = torch.cat(self._predicted_samples).cpu().numpy()
-        test_result = ss.ks_2samp(predicted_samples, reference_samples, alternative="two-sided", method="auto")
-        return test_result.statistic, test_result.pvalue
+        """(KS statistic, p-value) of scipy's two-sided two-sample test, predicted vs reference."""
+        reference = torch.cat(self._reference_samples).cpu().numpy()
+        predicted = torch.cat(self._predicted_samples).cpu().numpy()
+        result = ss.ks_2samp(predicted, reference, alternative="two-sided", method="auto")
+        return result.statistic, result.pvalue

@@ -65,8 +65,31 @@ class _Opaque:
             self.__dict__.update(state)
 
 
+# Globals a checkpoint may legitimately reference besides the reference package: tensor storage / rebuild helpers,
+# containers, numpy scalars and paths.  Anything else (os.system, builtins.eval, ...) becomes an inert _Opaque holder:
+# loading a checkpoint must never execute code it names.
+_ALLOWED_GLOBALS = {
+    "collections": {"OrderedDict", "defaultdict"},
+    "builtins": {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "complex", "slice",
+                 "range", "bytearray", "object"},
+    "pathlib": {"Path", "PosixPath", "PurePath", "PurePosixPath", "WindowsPath", "PureWindowsPath"},
+    "torch": {"Size", "device", "dtype", "Tensor", "FloatStorage", "DoubleStorage", "LongStorage", "IntStorage",
+              "HalfStorage", "BFloat16Storage", "BoolStorage", "ByteStorage", "CharStorage", "ShortStorage",
+              "float32", "float64", "float16", "bfloat16", "int64", "int32", "int16", "int8", "uint8", "bool"},
+    "torch._utils": {"_rebuild_tensor_v2", "_rebuild_tensor", "_rebuild_parameter", "_rebuild_parameter_with_state"},
+    "torch.storage": {"_load_from_bytes", "TypedStorage", "UntypedStorage"},
+    "torch.serialization": {"_get_layout"},
+    "torch.nn.parameter": {"Parameter"},
+    "numpy": {"ndarray", "dtype", "float32", "float64", "int64", "int32", "bool_"},
+    "numpy.core.multiarray": {"scalar", "_reconstruct"},
+    "numpy._core.multiarray": {"scalar", "_reconstruct"},
+    "dataclasses": {"_HAS_DEFAULT_FACTORY_CLASS"},
+}
+
+
 class _TolerantUnpickler(pickle.Unpickler):
-    """Resolves reference classes to this package's equivalents when they exist, to an opaque holder otherwise."""
+    """Resolves reference classes to this package's equivalents when they exist, allow-listed library globals to
+    themselves, and everything else to an inert opaque holder."""
 
     def find_class(self, module, name):
         if module == REFERENCE_PACKAGE or module.startswith(REFERENCE_PACKAGE + "."):
@@ -75,10 +98,12 @@ class _TolerantUnpickler(pickle.Unpickler):
                 return super().find_class(mirrored, name)
             except (ImportError, AttributeError):
                 return type(name, (_Opaque,), {})
-        try:
-            return super().find_class(module, name)
-        except (ImportError, AttributeError):
-            return type(name, (_Opaque,), {})
+        if name in _ALLOWED_GLOBALS.get(module, ()):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                pass
+        return type(name, (_Opaque,), {})
 
 
 class _TolerantPickle:
@@ -93,7 +118,7 @@ class _TolerantPickle:
 def _load_checkpoint_file(checkpoint_path: Union[str, Path]) -> Any:
     try:
         return torch.load(checkpoint_path, map_location="cpu", weights_only=True)
-    except Exception:  # a Lightning checkpoint with pickled hyper-parameter objects
+    except pickle.UnpicklingError:  # a Lightning checkpoint with pickled hyper-parameter objects (I/O errors propagate)
         return torch.load(checkpoint_path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
 
 

@@ -22,10 +22,14 @@ def get_coordinates_sigma_normalized_score(
         "The relative_coordinates and sigmas inputs should have the same shape"
     assert sigmas.device == relative_coordinates.device, "relative_coordinates and sigmas should be on the same device."
     device = _cabi.require_cuda(relative_coordinates, sigmas)
-    assert (sigmas > 0).all(), "All values of sigma should be larger than zero."
+    # the reference's two value asserts (:170-178) as ONE host synchronisation: a 2-bit code reduced on the device
+    code = (sigmas <= 0).any().to(torch.int32)
     if coordinates_bounded:
-        assert torch.logical_and(relative_coordinates >= 0, relative_coordinates < 1).all(), \
-            "the relative coordinates should all be in [0, 1)"
+        outside = torch.logical_or(relative_coordinates < 0, relative_coordinates >= 1).any().to(torch.int32)
+        code = code + 2 * outside
+    code = int(code.item())
+    assert not code & 1, "All values of sigma should be larger than zero."
+    assert not code & 2, "the relative coordinates should all be in [0, 1)"
     dtype = relative_coordinates.dtype
     if dtype not in (torch.float32, torch.float64):
         raise _cabi.B200MDError("wrapped Gaussian score supports float32 and float64")

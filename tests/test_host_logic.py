@@ -172,3 +172,32 @@ def test_trajectory_initializer_factory(tmp_path):
     assert torch.equal(init.initialize(4, torch.device("cpu")).X, start.X)
     with pytest.raises(AssertionError):
         init.initialize(5, torch.device("cpu"))
+
+
+def test_checkpoint_unpickler_never_executes_named_globals(tmp_path):
+    """A checkpoint that names an arbitrary callable (``os.system``) loads as an inert holder: only the reference package
+    (mapped to this package or to an opaque stand-in) and an allow-list of tensor / container globals are resolved."""
+    import io
+    import os
+    import pickle
+
+    from diffusion_for_multi_scale_molecular_dynamics_b200 import sample_diffusion
+
+    marker = tmp_path / "executed"
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, (f"touch {marker}",))
+
+    buffer = io.BytesIO()
+    pickle.dump({"payload": Evil(), "fine": {"a": 1}}, buffer)
+    buffer.seek(0)
+    loaded = sample_diffusion._TolerantUnpickler(buffer).load()
+    assert not marker.exists() and loaded["fine"] == {"a": 1}
+    assert isinstance(loaded["payload"], sample_diffusion._Opaque)
+    # the Lightning-like fixture (reference classes + tensors) still loads, and a missing file is an I/O error, not a fallback
+    checkpoint = sample_diffusion._load_checkpoint_file(os.path.join(os.path.dirname(__file__), "golden",
+                                                                    "lightning_like_checkpoint.ckpt"))
+    assert "state_dict" in checkpoint and sample_diffusion._find_score_network_parameters(checkpoint) is not None
+    with pytest.raises(FileNotFoundError):
+        sample_diffusion._load_checkpoint_file(tmp_path / "missing.ckpt")
