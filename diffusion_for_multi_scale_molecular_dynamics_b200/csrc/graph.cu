@@ -57,7 +57,7 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
       const float xi = px[i], yi = py[i], zi = pz[i];
       const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
       int deg = 0;
-      if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) {   // no atom of this image can be inside the cutoff
+      if (!image_can_hit(&s_cull, xi, yi, zi, img, rc)) {   // no atom of this image can be inside the cutoff
         if (lane == 0) counts[(b * 27 + img) * N + i] = 0;
         continue;
       }
@@ -122,7 +122,7 @@ __global__ void radius_graph_fill_kernel(const float* __restrict__ positions, co
       const float xi = px[i], yi = py[i], zi = pz[i];
       const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
       int cnt = 0;
-      if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) continue;   // an empty row (its count is 0)
+      if (!image_can_hit(&s_cull, xi, yi, zi, img, rc)) continue;   // an empty row (its count is 0)
       for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;
         bool hit = false;

@@ -114,6 +114,19 @@ __device__ __forceinline__ unsigned image_candidates(const ImageCull* c, float x
     if (((axis_ok[0] >> (img / 9)) & (axis_ok[1] >> ((img / 3) % 3)) & (axis_ok[2] >> (img % 3))) & 1u) mask |= 1u << img;
   return mask;
 }
+// The same test for ONE image (the per-image row loops): three dot products instead of the whole 27-bit mask.
+__device__ __forceinline__ bool image_can_hit(const ImageCull* c, float xi, float yi, float zi, int img, float rc) {
+  if (!B200MD_IMAGE_CULL) return true;
+  const float limit = rc * 1.01f;
+  const int n[3] = {img / 9 - 1, (img / 3) % 3 - 1, img % 3 - 1};
+  bool ok = true;
+  for (int k = 0; k < 3; ++k) {
+    const float s = xi * c->b[3 * k] + yi * c->b[3 * k + 1] + zi * c->b[3 * k + 2];
+    const float gap = fmaxf(fmaxf(cull_decode(c->smin[k]) + (float)n[k] - s, s - cull_decode(c->smax[k]) - (float)n[k]), 0.0f) * c->h[k];
+    ok = ok && !(gap > limit);
+  }
+  return ok;
+}
 // first hit among the candidate images, in image order (the image whose shift the reference reports)
 __device__ __forceinline__ int first_image_hit_among(float xi, float yi, float zi, float xj, float yj, float zj,
                                                      const float* __restrict__ lat, float rc2, unsigned candidates) {

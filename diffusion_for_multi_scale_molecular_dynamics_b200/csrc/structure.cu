@@ -39,7 +39,7 @@ __global__ void pair_distances_count_kernel(const float* __restrict__ positions,
     const float xi = px[i], yi = py[i], zi = pz[i];
     const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
     int n = 0;
-    if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) {
+    if (!image_can_hit(&s_cull, xi, yi, zi, img, rc)) {
       if (lane == 0) counts[(b * 27 + img) * N + i] = 0;
       continue;
     }
@@ -80,7 +80,7 @@ __global__ void pair_distances_fill_kernel(const float* __restrict__ positions, 
     const float xi = px[i], yi = py[i], zi = pz[i];
     const float lx = lat[img * 3], ly = lat[img * 3 + 1], lz = lat[img * 3 + 2];
     int cnt = 0;
-    if (!((image_candidates(&s_cull, xi, yi, zi, rc) >> img) & 1u)) continue;   // an empty row
+    if (!image_can_hit(&s_cull, xi, yi, zi, img, rc)) continue;   // an empty row
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int j = j0 + lane;
       bool hit = false;
