@@ -280,10 +280,19 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     generator._begin_trajectory(device)
     composition = generator.initialize(samples, device)
     index = TOTAL_TIME_STEPS
-    for _ in range(W):
-        composition = generator.sample_from_noisy_composition(composition, index, index - 1)
-        index -= 1
+    # warm-up exactly like the timed region: one call of W steps (W >= 3, so the captured step graph is exercised too)
+    composition = generator.sample_from_noisy_composition(composition, index, index - W)
+    index -= W
     edges_per_structure = measure_edges(network, composition, device)
+
+    def gather_axl(axl):
+        """The single collective of the path: all_gather of the sampled (A, X, L)."""
+        for part in (axl.A, axl.X, axl.L):
+            gathered = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(gathered, part.contiguous())
+
+    if world > 1:
+        gather_axl(composition)   # warm-up of the collective too (NCCL builds its channels on the first call per shape)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches_before = _cabi.launch_count()
@@ -294,10 +303,8 @@ def run_b200_arm(args, rank: int, world: int, local_rank: int):
     # b200md_pc_sample): no host synchronisation between steps
     composition = generator.sample_from_noisy_composition(composition, index, index - K)
     index -= K
-    if world > 1:  # the single collective of the path: final all-gather of the sampled AXL
-        for part in (composition.A, composition.X, composition.L):
-            gathered = [torch.empty_like(part) for _ in range(world)]
-            dist.all_gather(gathered, part.contiguous())
+    if world > 1:
+        gather_axl(composition)
     stop.record()
     barrier()
     ms_total = max_over_ranks(start.elapsed_time(stop))

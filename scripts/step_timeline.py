@@ -53,6 +53,11 @@ for before, after in zip(events, events[1:]):
 print("# idle gap between consecutive kernels (us): count, mean, max, total")
 for (a, b), values in sorted(gaps.items(), key=lambda kv: -sum(kv[1])):
     print(f"{len(values):5d} {sum(values) / len(values):9.1f} {max(values):9.1f} {sum(values):10.1f}   {a} -> {b}")
+print("# every launch of the first step (us): start offset, duration, name")
+t0 = events[0].time_range.start
+per_step = len(events) // args.steps
+for e in events[: per_step + 2]:
+    print(f"{e.time_range.start - t0:12.1f} {e.time_range.end - e.time_range.start:10.1f}   {e.name[:70]}")
 durations = collections.defaultdict(list)
 for e in events:
     durations[e.name[:60]].append(e.time_range.end - e.time_range.start)
