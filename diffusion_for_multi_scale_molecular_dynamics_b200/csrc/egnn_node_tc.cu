@@ -282,6 +282,22 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_node_tc_kernel(const NodeTcA
 
 }  // namespace
 
+#ifdef B200MD_TS_TRACE
+}  // namespace b200md
+// debug only: copy the cycle trace of the traced egnn_node_ts_kernel launch to the host and reset it
+extern "C" int b200md_debug_node_trace(unsigned* out_records_u4, int max_records) {
+  unsigned n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, b200md::g_node_trace_count, sizeof(n));
+  if ((int)n > max_records) n = max_records;
+  cudaMemcpyFromSymbol(out_records_u4, b200md::g_node_trace, sizeof(uint4) * n);
+  unsigned zero = 0;
+  cudaMemcpyToSymbol(b200md::g_node_trace_count, &zero, sizeof(zero));
+  return (int)n;
+}
+namespace b200md {
+#endif
+
 bool tc_node_supported(const b200md_egnn_config& cfg, int precision) {
   const int H = cfg.node_hidden, M = cfg.message_hidden;
   const int chunk = precision == kTf32x3 ? 32 : 64;
@@ -405,6 +421,7 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
     t.residual = a.residual; t.coords_mean = a.coords_mean; t.message_mean = a.message_mean; t.mask_logit = call.mask_logit;
     t.bloch = lay.bloch; t.proj = lay.proj; t.embed_w = lay.embed_w; t.embed_b = lay.embed_b;
     t.readout_w = lay.readout_w; t.readout_b = lay.readout_b;
+    t.trace = (call.update_layer == 1 && call.pq_layer >= 0) ? 1 : 0;
     const size_t ts_bytes = node_ts_smem(n).total + 1024;
     static PerDeviceOnce ts_attr_set;
     if (ts_attr_set.needed()) {

@@ -20,6 +20,10 @@
 
 #include "ts_common.cuh"
 
+#ifndef B200MD_NODE_TS_PIPELINED
+#define B200MD_NODE_TS_PIPELINED 1
+#endif
+
 enum NodeGemmKind {
   kNodeChain = 0,       // v = silu(acc + bias)                      -> next A
   kNodeChainAddU = 1,   // v = silu(acc + U[node])                   -> next A
@@ -54,18 +58,51 @@ struct NodeTsArgs {
   int C, F0, D, H, M, nb;
   int residual, coords_mean, message_mean, mask_logit;
   int64_t bloch, proj, embed_w, embed_b, readout_w, readout_b;
+  int trace;   // B200MD_TS_TRACE builds: record the cycle trace of this launch
 };
 
 constexpr int kNodeMaxClasses = 8;
 
+// Optional cycle trace of CTA 0 (build with -DB200MD_TS_TRACE; read back with b200md_debug_node_trace, scripts/node_trace.py):
+// one record (warp, event, argument, clock) per NODE_TRACE call of lane 0 of the MMA warp and of the two epilogue warps
+// of lane quarter 0, for the launch that updates layer 1 (update + P / Q / U outputs).
+#ifdef B200MD_TS_TRACE
+constexpr unsigned kNodeTraceRecords = 4096;
+__device__ uint4 g_node_trace[3 * kNodeTraceRecords];
+__device__ unsigned g_node_trace_count;
+#define NODE_TRACE(ev, arg)                                                                                     \
+  do {                                                                                                          \
+    if (trace_on && trace_idx < kNodeTraceRecords) {                                                            \
+      g_node_trace[trace_slot * kNodeTraceRecords + trace_idx] = make_uint4((unsigned)warp, (unsigned)(ev), (unsigned)(arg), (unsigned)clock()); \
+      ++trace_idx;                                                                                              \
+    }                                                                                                           \
+  } while (0)
+#else
+#define NODE_TRACE(ev, arg) do { } while (0)
+#endif
+
+// Weight ring of the node kernel: 10 stages of 16 KB (the 12 of ts_common.cuh minus the 32 KB of row staging below; the
+// producer is always ahead of the MMAs -- it waits on "stage empty" for most of its life -- so two stages less cost nothing).
+constexpr int kNodeBStages = 10;
+static_assert(kNodeBStages % 2 == 0, "the MMA loop consumes the hi / lo stages of a K chunk in pairs");
+// Row staging: 32 rows x 128 B per epilogue warp.  A TMEM lane is a ROW, so an epilogue thread owns 128 contiguous bytes
+// of one row and a warp-wide 128-bit access touches 32 different lines: 32 L1 wavefronts per instruction, 2048 per 64-column
+// chunk and SM, and the tile's 32 chunk-sized row accesses (agg, U, h in; agg reset, h, P, Q, U out) cost 65 k of its
+// 149 k cycles (cycle trace, scripts/node_trace.py).  Through the staging tile every global access is made by 8 lanes per
+// 128-byte line (4 lines per instruction): 8 x fewer wavefronts.  XOR-swizzled 16-byte pieces, conflict-free both ways.
+#ifndef B200MD_NODE_TS_COALESCED
+#define B200MD_NODE_TS_COALESCED 1
+#endif
+constexpr int kNodeStageBytes = 32 * 128;
 struct NodeTsSmem {
-  uint32_t b, bars, tmem_slot, bias, scale, readout, logits, total;
+  uint32_t b, stage, bars, tmem_slot, bias, scale, readout, logits, total;
 };
 __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   NodeTsSmem L;
   uint32_t o = 0;
-  L.b = o; o += kTsBStages * kTsBStageBytes;
-  L.bars = o; o += (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit + kTsNSplit) * 8;
+  L.b = o; o += kNodeBStages * kTsBStageBytes;
+  L.stage = o; o += kTsEpiWarps * kNodeStageBytes;
+  L.bars = o; o += (2 * kNodeBStages + kTsSlots * kTsParts + 2 * kTsNSplit + kTsNSplit) * 8;
   L.tmem_slot = o; o += 16;
   o = (o + 15u) & ~15u;   // the bias rows are read with 128-bit shared loads
   L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
@@ -79,19 +116,24 @@ __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
 struct NodeTsBars {
   uint32_t bar0;
   __device__ __forceinline__ uint32_t b_full(uint32_t s) const { return bar0 + 8u * s; }
-  __device__ __forceinline__ uint32_t b_empty(uint32_t s) const { return bar0 + 8u * (kTsBStages + s); }
+  __device__ __forceinline__ uint32_t b_empty(uint32_t s) const { return bar0 + 8u * (kNodeBStages + s); }
   __device__ __forceinline__ uint32_t a_full(uint32_t slot, uint32_t part) const {
-    return bar0 + 8u * (2 * kTsBStages + slot * kTsParts + part);
+    return bar0 + 8u * (2 * kNodeBStages + slot * kTsParts + part);
   }
   __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
-    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
+    return bar0 + 8u * (2 * kNodeBStages + kTsSlots * kTsParts + buf * kTsNSplit + group);
   }
   // "column group `group` of the output accumulator has been drained"
   __device__ __forceinline__ uint32_t d_free(uint32_t group) const {
-    return bar0 + 8u * (2 * kTsBStages + kTsSlots * kTsParts + 2 * kTsNSplit + group);
+    return bar0 + 8u * (2 * kNodeBStages + kTsSlots * kTsParts + 2 * kTsNSplit + group);
   }
 };
 
+__device__ __forceinline__ float4 lds128_staged(uint32_t saddr) {   // ordered against the staging stores (volatile, clobber)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void load_cols(const float* p, float (&v)[kTsCols]) {
 #pragma unroll
   for (int j = 0; j < kTsCols / 4; ++j) {
@@ -129,7 +171,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
   NodeTsBars bars;
   bars.bar0 = s_base + L.bars;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsBStages; ++s) { mbar_init(bars.b_full(s), 1); mbar_init(bars.b_empty(s), 1); }
+    for (int s = 0; s < kNodeBStages; ++s) { mbar_init(bars.b_full(s), 1); mbar_init(bars.b_empty(s), 1); }
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(bars.a_full(s, j), 4);
     for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(bars.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
@@ -142,6 +184,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
   tc_fence_after();
   const uint32_t tmem_base_all = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
   const int n_iterations = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+#ifdef B200MD_TS_TRACE
+  bool trace_on = false;
+  unsigned trace_idx = 0;
+  const unsigned trace_slot = warp == 1 ? 0u : (warp == kTsFirstEpiWarp ? 1u : 2u);
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) g_node_trace_count = 3 * kNodeTraceRecords;
+#endif
 
   if (warp < kTsFirstEpiWarp) {   // setmaxnreg at the top of each warpgroup's branch (see egnn_edge_ts.cuh)
 #if B200MD_TS_WARPGROUPS
@@ -160,8 +208,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           const float* src = a.wtc + G.w16;
           for (int h = 0; h < kTsNSplit; ++h)
             for (int part = 0; part < 2 * nk; ++part, ++cb) {
-              const uint32_t s = cb % kTsBStages;
-              mbar_wait(bars.b_empty(s), ((cb / kTsBStages) & 1u) ^ 1u);
+              const uint32_t s = cb % kNodeBStages;
+              mbar_wait(bars.b_empty(s), ((cb / kNodeBStages) & 1u) ^ 1u);
               mbar_arrive_expect_tx(bars.b_full(s), bytes);
               bulk_g2s(s_base + L.b + s * kTsBStageBytes, src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4),
                        bytes, bars.b_full(s));
@@ -178,24 +226,32 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     (void)use0; (void)use1;
     for (int it = 0; it < n_iterations; ++it)
       for (int g = 0; g < a.n_gemms; ++g) {
+#ifdef B200MD_TS_TRACE
+        trace_on = (a.trace && blockIdx.x == 0 && lane == 0 && it >= 2 && it < 4);
+#endif
         const NodeTsGemm& G = a.g[g];
         const int nk = G.K / 64, nh = G.N / kTsNSplit;
         const uint32_t idesc = make_idesc(nh, 0u);
         const uint32_t a_col = abuf * kMaxN, d_col = a_col ^ kMaxN;
         for (int h = 0; h < kTsNSplit; ++h) {
+          NODE_TRACE(130 + h, g);
           if (G.wait_d_free) { mbar_wait(bars.d_free(h), df & 1u); tc_fence_after(); }
+          NODE_TRACE(140 + h, g);
           const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
           for (int c = 0; c < nk; ++c) {
-            const uint32_t s1 = cb % kTsBStages, s2 = (cb + 1) % kTsBStages;
-            mbar_wait(bars.b_full(s1), (cb / kTsBStages) & 1u);
-            mbar_wait(bars.b_full(s2), ((cb + 1) / kTsBStages) & 1u);
+            const uint32_t s1 = cb % kNodeBStages, s2 = (cb + 1) % kNodeBStages;
+            mbar_wait(bars.b_full(s1), (cb / kNodeBStages) & 1u);
+            mbar_wait(bars.b_full(s2), ((cb + 1) / kNodeBStages) & 1u);
             const uint32_t bd1 = desc_lo_sw128(b_ring + s1 * kTsBStageBytes), bd2 = desc_lo_sw128(b_ring + s2 * kTsBStageBytes);
             const uint32_t chunk = mca + (uint32_t)c;
             const uint32_t a_chunk = tmem_base + a_col + (uint32_t)(c * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (G.fresh_a && h == 0 && (j % (4 / kTsParts)) == 0)
+              if (G.fresh_a && h == 0 && (j % (4 / kTsParts)) == 0) {
+                NODE_TRACE(100 + j, g * 16 + c);
                 mbar_wait(bars.a_full(chunk % kTsSlots, j / (4 / kTsParts)), (chunk / kTsSlots) & 1u);
+                NODE_TRACE(110 + j, g * 16 + c);
+              }
               tc_fence_after();
               if (leader) {
                 umma_f16_ts(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);
@@ -212,6 +268,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           }
           if (leader) umma_commit(bars.acc_full(d_col / kMaxN, h));
           __syncwarp();
+          NODE_TRACE(120 + h, g);
         }
         if (G.wait_d_free) ++df;
         if (G.fresh_a) mca += nk;
@@ -230,10 +287,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base_all + ((uint32_t)(q * 32) << 16);
     const uint32_t sa_bias = s_base + L.bias;
+    const uint32_t stage = s_base + L.stage + (uint32_t)(warp - kTsFirstEpiWarp) * kNodeStageBytes;
     uint32_t ca = 0, abuf = 0;
     uint32_t uses[2] = {0u, 0u};
     unsigned local_status = 0;
     float checksum = 0.f;   // inf / NaN of an fp16 overflow propagates into everything stored: one test at the end
+#if B200MD_NODE_TS_PIPELINED
+    const uint32_t tok_mine = 2u + 2u * (uint32_t)q + (uint32_t)part, tok_peer = 2u + 2u * (uint32_t)q + (uint32_t)(part ^ 1);
+    if (part == 1) sfu_arrive(tok_peer);   // part 0 goes first
+#endif
 
     // `scale`: kF16ActScale for values that are not scaled yet (every A operand is stored x kF16ActScale), 1 for the
     // outputs of the SiLU layers, which already are
@@ -253,10 +315,88 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     };
 
     for (int it = 0; it < n_iterations; ++it) {
+#ifdef B200MD_TS_TRACE
+      trace_on = (a.trace && blockIdx.x == 0 && lane == 0 && q == 0 && it >= 2 && it < 4);
+#endif
+      NODE_TRACE(20, it);
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int64_t node = (int64_t)tile * kTileM + row;
       const bool valid = node < a.n_nodes;
       const float degf = valid ? fmaxf((float)a.deg[node], 1.0f) : 1.0f;
+      // ---- warp-cooperative row access through the staging tile (see kNodeStageBytes) ----
+      const int64_t warp_row0 = (int64_t)tile * kTileM + q * 32;   // node of lane 0's row
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.n_nodes - warp_row0));   // warp-uniform
+      const int crow = lane >> 3, cpiece = lane & 7;   // cooperative role: instruction i covers rows 4 i + crow, piece cpiece
+      struct RowTile { float4 p[8]; };
+      // request columns [col, col + 32) of the warp's 32 rows of `rows` (row stride ld floats) ...
+      auto rows_request = [&](const float* rows, int ld, int col, RowTile& t) {
+#if B200MD_NODE_TS_COALESCED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int R = 4 * i + crow;
+          t.p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rows != nullptr && R < rows_valid) t.p[i] = *(reinterpret_cast<const float4*>(rows + (warp_row0 + R) * ld + col) + cpiece);
+        }
+#else
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          t.p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rows != nullptr && valid) t.p[i] = *(reinterpret_cast<const float4*>(rows + node * ld + col) + i);
+        }
+#endif
+      };
+      // ... and turn the requested tile into this lane's own row (rows beyond the end read as zero)
+      auto rows_collect = [&](const RowTile& t, float (&v)[kTsCols]) {
+#if B200MD_NODE_TS_COALESCED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int R = 4 * i + crow;
+          sts128(stage + (uint32_t)R * 128u + (uint32_t)((cpiece ^ (R & 7)) << 4), t.p[i].x, t.p[i].y, t.p[i].z, t.p[i].w);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float4 f = lds128_staged(stage + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4));
+          v[4 * p] = f.x; v[4 * p + 1] = f.y; v[4 * p + 2] = f.z; v[4 * p + 3] = f.w;
+        }
+        __syncwarp();
+#else
+#pragma unroll
+        for (int p = 0; p < 8; ++p) { v[4 * p] = t.p[p].x; v[4 * p + 1] = t.p[p].y; v[4 * p + 2] = t.p[p].z; v[4 * p + 3] = t.p[p].w; }
+#endif
+      };
+      // store this lane's row values as columns [col, col + 32) of the warp's rows of `rows`
+      auto rows_store = [&](float* rows, int ld, int col, const float (&v)[kTsCols]) {
+#if B200MD_NODE_TS_COALESCED
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          sts128(stage + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4), v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int R = 4 * i + crow;
+          const float4 f = lds128_staged(stage + (uint32_t)R * 128u + (uint32_t)((cpiece ^ (R & 7)) << 4));
+          if (R < rows_valid) *(reinterpret_cast<float4*>(rows + (warp_row0 + R) * ld + col) + cpiece) = f;
+        }
+        __syncwarp();
+#else
+        if (valid) store_cols(rows + node * ld + col, v);
+#endif
+      };
+      auto rows_zero = [&](float* rows, int ld, int col) {
+#if B200MD_NODE_TS_COALESCED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int R = 4 * i + crow;
+          if (R < rows_valid) *(reinterpret_cast<float4*>(rows + (warp_row0 + R) * ld + col) + cpiece) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#else
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *(reinterpret_cast<float4*>(rows + node * ld + col) + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#endif
+      };
       float sg = 0.f;
       int atc = 0;
       if (a.do_embed && valid) {
@@ -287,15 +427,29 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             a.xagg[node * D + 2 * b] = 0.f; a.xagg[node * D + 2 * b + 1] = 0.f;
           }
         }
-        if (a.do_update) {  // coord += agg   models/egnn.py:212-215
-          for (int d = 0; d < D; ++d) {
-            float v = a.xagg[node * D + d];
-            if (a.coords_mean) v = v / degf;
-            a.xcur[node * D + d] += v;
-            a.xagg[node * D + d] = 0.f;
-          }
-        }
       }
+      // coord += agg (models/egnn.py:212-215).  Nothing in this tile's GEMMs depends on it, so it runs BEHIND the first A
+      // operand (while the first MMAs execute), and all its loads are issued before the first store: written as one
+      // load-add-store-store per coordinate it is a chain of 2 D dependent memory round trips (the compiler cannot prove
+      // that xagg and xcur do not alias) that sat in front of the tile's first MMA for 20 k cycles (cycle trace).
+      auto coordinate_update = [&]() {
+        if (!(a.do_update && part == 0 && valid)) return;
+        for (int d0 = 0; d0 < D; d0 += 8) {
+          float xa[8], xc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            xa[k] = (d0 + k < D) ? a.xagg[node * D + d0 + k] : 0.f;
+            xc[k] = (d0 + k < D) ? a.xcur[node * D + d0 + k] : 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (d0 + k < D) {
+              const float v = a.coords_mean ? xa[k] / degf : xa[k];
+              a.xcur[node * D + d0 + k] = xc[k] + v;
+              a.xagg[node * D + d0 + k] = 0.f;
+            }
+        }
+      };
 
       // ---- first A operand of the tile ----
       const uint32_t a_col0 = abuf * kMaxN;
@@ -309,47 +463,31 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             const int o = col0 + j;
             v[j] = valid ? Wp[a.embed_b + o] + (Wp[a.embed_w + o * a.F0] * sg + Wp[a.embed_w + o * a.F0 + 1 + atc]) : 0.f;
           }
-          if (valid) store_cols(a.h + node * H + col0, v);
+          rows_store(a.h, H, col0, v);
           publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
         }
-        if (valid) {
-          float zero[kTsCols];
-#pragma unroll
-          for (int j = 0; j < kTsCols; ++j) zero[j] = 0.f;
-          for (int c = 0; c < M / 64; ++c) store_cols(a.agg + node * M + c * 64 + part * kTsCols, zero);
-        }
+        for (int c = 0; c < M / 64; ++c) rows_zero(a.agg, M, c * 64 + part * kTsCols);
       } else {
         // aggregated messages (mean: / max(deg, 1)), reset for the next layer   models/egnn.py:178-183
         // (the rows of chunk c + 1 are requested before chunk c is converted and published)
-        float ahead[kTsCols];
-#pragma unroll
-        for (int j = 0; j < kTsCols; ++j) ahead[j] = 0.f;
-        if (valid) load_cols(a.agg + node * M + part * kTsCols, ahead);
+        RowTile ahead;
+        rows_request(a.agg, M, part * kTsCols, ahead);
         for (int c = 0; c < M / 64; ++c) {
           const int col0 = c * 64 + part * kTsCols;
           float v[kTsCols];
-          if (valid) {
-            float* ap = a.agg + node * M + col0;
+          rows_collect(ahead, v);   // the loads have returned here: the reset below may follow (a store issued right
+                                    // behind loads of the same addresses doubles the time of the whole kernel, measured)
+          if (c + 1 < M / 64) rows_request(a.agg, M, col0 + 64, ahead);
+          if (a.message_mean) {
 #pragma unroll
-            for (int j = 0; j < kTsCols; ++j) v[j] = ahead[j];
-            if (c + 1 < M / 64) load_cols(ap + 64, ahead);
-            if (a.message_mean) {
-#pragma unroll
-              for (int j = 0; j < kTsCols; ++j) v[j] = v[j] / degf;
-            }
-            float zero[kTsCols];
-#pragma unroll
-            for (int j = 0; j < kTsCols; ++j) zero[j] = 0.f;
-            // Keep this store AFTER the division above (i.e. after the loads have returned): issued right behind the
-            // loads of the same addresses it doubles the time of the whole kernel (12 -> 25 ms per step, measured).
-            store_cols(ap, zero);
-          } else {
-#pragma unroll
-            for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
+            for (int j = 0; j < kTsCols; ++j) v[j] = v[j] / degf;
           }
+          rows_zero(a.agg, M, col0);
           publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
+          NODE_TRACE(21, c);
         }
       }
+      coordinate_update();
 
       // ---- the GEMMs ----
       float logit[kNodeMaxClasses];
@@ -371,28 +509,87 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         // the rows this epilogue adds to the accumulator (U, or the residual h) travel one chunk ahead of their use:
         // the L2 / HBM round trip of chunk c + 1 is hidden behind the conversion of chunk c (and, for chunk 0,
         // behind the wait for the accumulator)
-        const float* side_rows = nullptr;
-        if (valid && G.kind == kNodeChainAddU) side_rows = a.U + node * H;
-        if (valid && G.kind == kNodeChainLast && a.residual) side_rows = a.h + node * H;
-        float side[kTsCols];
-#pragma unroll
-        for (int j = 0; j < kTsCols; ++j) side[j] = 0.f;
-        if (side_rows) load_cols(side_rows + part * kTsCols, side);
-        for (int c = 0; c < nchunks; ++c) {
+        const float* side_rows = nullptr;   // warp-uniform
+        if (G.kind == kNodeChainAddU) side_rows = a.U;
+        if (G.kind == kNodeChainLast && a.residual) side_rows = a.h;
+        RowTile side_tile;
+        rows_request(side_rows, H, part * kTsCols, side_tile);
+        auto wait_for_chunk = [&](int c) {
           const int need = ts_last_group_of_chunk(c, nh);
           if (need > waited) {
+            NODE_TRACE(1, g * 16 + c);
             mbar_wait(bars.acc_full(dbuf, need), uses[dbuf] & 1u);
             tc_fence_after();
             waited = need;
+            NODE_TRACE(2, g * 16 + c);
           }
+        };
+#if B200MD_NODE_TS_PIPELINED
+        if (G.kind == kNodeChain || G.kind == kNodeChainAddU) {
+          // The SiLU layers bound this kernel (the MMA warp spends most of its time waiting for A chunks, the cycle samples
+          // of profiles/ncu_full_r02a say): same chunk pipeline as the edge kernel.  The accumulator columns of chunk
+          // c + 1 are requested (tcgen05.ld) before chunk c is split and published and collected afterwards, and the two
+          // epilogue warps of a scheduler alternate in the SFU-bound SiLU phase (token: ts_common.cuh).
+          float v[kTsCols];
+          uint32_t r[kTsCols];
+          auto activate = [&](int c) {
+            const int col0 = c * 64 + part * kTsCols;
+            uint32_t dep = 0;
+            if (G.kind == kNodeChain) {
+#pragma unroll
+              for (int j = 0; j < kTsCols / 4; ++j) {
+                const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
+                silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1], dep);
+                silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3], dep);
+              }
+            } else {
+#pragma unroll
+              float side[kTsCols];
+              rows_collect(side_tile, side);
+              if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);   // U of the next chunk
+#pragma unroll
+              for (int j = 0; j < kTsCols / 2; ++j)
+                silu2_dep(fma2(pack2(side[2 * j], side[2 * j + 1]), pack2(kF16ActScale, kF16ActScale),
+                               mul2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), unscale2)), v[2 * j], v[2 * j + 1], dep);
+            }
+            sfu_release(tok_peer, dep);
+          };
+          auto load_acc = [&](int c) {
+#pragma unroll
+            for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(lane_taddr + d_col + c * 64 + part * kTsCols + 16 * i, r + 16 * i);
+          };
+          auto collect_acc = [&]() {
+            sfu_acquire(tok_mine);
+#pragma unroll
+            for (int i = 0; i < kTsCols / 16; ++i) tmem_ld_wait16(r + 16 * i);
+          };
+          wait_for_chunk(0);
+          load_acc(0);
+          collect_acc();
+          activate(0);
+          for (int c = 0; c < nchunks; ++c) {
+            const bool more = c + 1 < nchunks;
+            if (more) { wait_for_chunk(c + 1); load_acc(c + 1); }
+            publish(d_col + (uint32_t)(c * 64 + part * kTsCols), v, 1.0f);
+            NODE_TRACE(6, g * 16 + c);
+            if (more) { collect_acc(); activate(c + 1); NODE_TRACE(5, g * 16 + c + 1); }
+          }
+          ++uses[dbuf];
+          abuf ^= 1u;
+          continue;
+        }
+#endif
+        for (int c = 0; c < nchunks; ++c) {
+          wait_for_chunk(c);
           const int col0 = c * 64 + part * kTsCols;
           uint32_t r[kTsCols];
           float v[kTsCols];
           tmem_load_cols(lane_taddr + d_col + col0, r);
           float u[kTsCols];
-#pragma unroll
-          for (int j = 0; j < kTsCols; ++j) u[j] = side[j];
-          if (side_rows && c + 1 < nchunks) load_cols(side_rows + col0 + 64, side);
+          if (side_rows != nullptr) {   // warp-uniform
+            rows_collect(side_tile, u);
+            if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);
+          }
           if (G.kind == kNodeChain) {
 #pragma unroll
             for (int j = 0; j < kTsCols / 4; ++j) {
@@ -415,13 +612,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), unscale_true, b.w);
             }
             if (G.kind == kNodeChainLast) {
-              if (valid) {
-                if (a.residual) {
+              if (a.residual) {
 #pragma unroll
-                  for (int j = 0; j < kTsCols; ++j) v[j] = u[j] + v[j];
-                }
-                store_cols(a.h + node * H + col0, v);
+                for (int j = 0; j < kTsCols; ++j) v[j] = u[j] + v[j];
               }
+              rows_store(a.h, H, col0, v);
               if (a.do_readout) {   // logits = W_c h + b_c (egnn.py:379): partial dot products while h' is in registers
 #pragma unroll
                 for (int cl = 0; cl < kNodeMaxClasses; ++cl)
@@ -436,8 +631,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                     logit[cl] += acc;
                   }
               }
-            } else if (valid) {
-              store_cols(G.out + node * G.N + col0, v);
+            } else {
+              rows_store(G.out, G.N, col0, v);
             }
             if (valid) {
 #pragma unroll
@@ -445,6 +640,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             }
           }
           if (becomes_a) publish(d_col + (uint32_t)col0, v, G.kind == kNodeChainLast ? kF16ActScale : 1.0f);
+          NODE_TRACE(30, g * 16 + c);
           if (G.signal_d_free) {   // every column group that ends inside this chunk is drained now
 #pragma unroll
             for (int h = 0; h < kTsNSplit; ++h)
@@ -487,6 +683,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         ts_epilogue_barrier();
       }
     }
+#if B200MD_NODE_TS_PIPELINED
+    if (part == 0) sfu_acquire(tok_mine);   // the peer's last release
+#endif
     if (!(fabsf(checksum) <= CUDART_MAX_NORMAL_F)) local_status |= B200MD_STATUS_TC_RANGE;
     if (local_status && a.status) atomicOr(a.status, (int)local_status);
   }
