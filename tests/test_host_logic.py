@@ -201,3 +201,42 @@ def test_checkpoint_unpickler_never_executes_named_globals(tmp_path):
     assert "state_dict" in checkpoint and sample_diffusion._find_score_network_parameters(checkpoint) is not None
     with pytest.raises(FileNotFoundError):
         sample_diffusion._load_checkpoint_file(tmp_path / "missing.ckpt")
+
+
+def test_auto_implementation_widens_its_range_once(monkeypatch):
+    """Host logic of the fp16-overflow fallback (no GPU): under IMPL_AUTO a TC_RANGE bit in the status word switches the
+    network to the 3xTF32 kernels for good, clears the word (bits raised downstream of the overflow are stale) and asks
+    the caller to evaluate again; a forced implementation keeps the bit, which is then raised as an AssertionError."""
+    from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+    from diffusion_for_multi_scale_molecular_dynamics_b200.models.score_networks.egnn_score_network import (
+        EGNNScoreNetwork, EGNNScoreNetworkParameters)
+    hp = dict(num_atom_types=1, edges="radial_cutoff", radial_cutoff=3.0, message_hidden_dimensions_size=64,
+              coordinate_hidden_dimensions_size=64, node_hidden_dimensions_size=64, n_layers=1)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
+    assert net.effective_kernel_impl() == _cabi.IMPL_AUTO and "3xFP16" in net.last_edge_kernel_name()
+    net._status = torch.tensor([_cabi.STATUS_TC_RANGE | _cabi.STATUS_BAD_LOGITS], dtype=torch.int32)
+    assert net.widen_range_after_overflow() is True
+    assert net.effective_kernel_impl() == _cabi.IMPL_TCGEN05 and "3xTF32" in net.last_edge_kernel_name()
+    assert int(net._status) == 0
+    net._status.fill_(_cabi.STATUS_TC_RANGE)
+    assert net.widen_range_after_overflow() is False   # already on the wide-range kernels: nothing left to fall back to
+    with pytest.raises(AssertionError, match="fp16 range"):
+        net.raise_on_device_status()
+    forced = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
+    forced.kernel_impl = _cabi.IMPL_TCGEN05_F16X3_TS
+    forced._status = torch.tensor([_cabi.STATUS_TC_RANGE], dtype=torch.int32)
+    assert forced.widen_range_after_overflow() is False and int(forced._status) == _cabi.STATUS_TC_RANGE
+    narrow = EGNNScoreNetwork(EGNNScoreNetworkParameters(num_atom_types=1))   # default widths: FFMA kernels, no fp16 anywhere
+    narrow._status = torch.tensor([_cabi.STATUS_TC_RANGE], dtype=torch.int32)
+    assert narrow.widen_range_after_overflow() is False
+
+
+def test_status_word_helpers():
+    from diffusion_for_multi_scale_molecular_dynamics_b200 import _cabi
+    assert _cabi.status_word(None) == 0
+    status = torch.tensor([_cabi.STATUS_X_OUT_OF_RANGE | _cabi.STATUS_MASK_REMAINS], dtype=torch.int32)
+    assert _cabi.status_word(status) == 17
+    with pytest.raises(AssertionError, match=r"\[0,1\)") as info:
+        _cabi.raise_for_word(17, status)
+    assert "MASKED" in str(info.value) and int(status) == 0
+    _cabi.raise_for_word(0, status)   # nothing set: no exception
