@@ -41,6 +41,11 @@ constexpr int kTsCluster = B200MD_TS_CLUSTER;
 #endif
 constexpr int kTsTokenReleaseAfter = B200MD_TS_TOKEN_RELEASE;
 
+// Reciprocals of the SiLU (ts_common.cuh: silu4): 0 = one per element, 1 = one per pair, 2 = one per four elements
+#ifndef B200MD_TS_EDGE_SILU
+#define B200MD_TS_EDGE_SILU 1
+#endif
+constexpr int kTsEdgeSilu = B200MD_TS_EDGE_SILU;
 // Column groups and weight ring of the edge kernel (the node kernel keeps ts_common.cuh's two groups and 12 stages).
 // One group = whole-width MMAs (N = 256): 139 cycles each against 2 x 75 for two halves, half as many instructions
 // and weight stages; it lost to two groups while the epilogue was the bound (20.4 vs 20.15 ms) and wins now that the
@@ -54,20 +59,32 @@ constexpr int kTsTokenReleaseAfter = B200MD_TS_TOKEN_RELEASE;
 #endif
 constexpr int kTsEdgeNSplit = B200MD_TS_EDGE_NSPLIT;
 constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes;
+// B200MD_TS_PQ_STAGE = 1: the P[src] / Q[dst] rows of the NEXT tile's first activation travel L2 -> shared memory with
+// cp.async (LDGSTS: no registers, no L1 lines held while in flight) into a private 2 x 128-byte slot per epilogue thread,
+// one chunk ahead of their use: chunk 0 is requested when the tile's last layer starts, chunk c + 1 when chunk c has been
+// read.  A thread reads only what it copied itself (cp.async.wait_all, no barrier).  The Q slots alias the staging tiles
+// of the segmented sum (idle between the message layer and the next tile's message layer); the P slots are paid for by
+// one weight stage (ring of 4).  Replaces the exposed L2 round trips of the gather at the tile boundary (cycle trace:
+// 19.6 k cycles for the last layer against 8.9 k for a plain one).
+#ifndef B200MD_TS_PQ_STAGE
+#define B200MD_TS_PQ_STAGE 0
+#endif
 #ifndef B200MD_TS_EDGE_STAGES
-#define B200MD_TS_EDGE_STAGES ((B200MD_TS_SEG_SMEM ? 11 : 12) * B200MD_TS_EDGE_NSPLIT / 2)
+#define B200MD_TS_EDGE_STAGES (((B200MD_TS_SEG_SMEM ? 11 : 12) * B200MD_TS_EDGE_NSPLIT / 2) - (B200MD_TS_PQ_STAGE ? B200MD_TS_EDGE_NSPLIT : 0))
 #endif
 constexpr int kTsEdgeBStages = B200MD_TS_EDGE_STAGES;
 constexpr int kTsSegTileBytes = 32 * kTsCols * 4;
 static_assert(!B200MD_TS_SEG_SMEM || kTsCols == 32, "segment_add maps one lane to one column");
+static_assert(!B200MD_TS_PQ_STAGE || (B200MD_TS_SEG_SMEM && kTsCols == 32), "the Q slots alias the segmented-sum tiles (32 x 128 B per warp)");
 struct TsSmem {
-  uint32_t b, seg, bars, tmem_slot, bias, scale, wr, wlast, dot, total;
+  uint32_t b, seg, pslot, bars, tmem_slot, bias, scale, wr, wlast, dot, total;
 };
 __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   TsSmem L;
   uint32_t o = 0;
   L.b = o; o += kTsEdgeBStages * kTsEdgeBStageBytes;
   L.seg = o; o += B200MD_TS_SEG_SMEM ? kTsEpiWarps * kTsSegTileBytes : 0;
+  L.pslot = o; o += B200MD_TS_PQ_STAGE ? kTsEpiWarps * kTsSegTileBytes : 0;
   L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsEdgeNSplit) * 8;
   L.tmem_slot = o; o += 16;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
@@ -275,6 +292,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     const uint32_t lane_taddr = pipe.tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t sa_bias = pipe.s_base + L.bias, sa_wr = pipe.s_base + L.wr, sa_wlast = pipe.s_base + L.wlast;
     uint32_t ca = 0, gc = 0;
+    uint32_t dep_first = 0;   // sink of silu4's token dependency where no token is passed
     bool poisoned = false;
 #if B200MD_TS_SFU_TOKEN
     const uint32_t tok_mine = 2u + 2u * (uint32_t)q + (uint32_t)part, tok_peer = 2u + 2u * (uint32_t)q + (uint32_t)(part ^ 1);
@@ -422,8 +440,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #pragma unroll
         for (int j = 0; j < kTsCols / 4; ++j) {
           const float4 pv = t.p[j], qv = t.q[j], wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
-          silu2(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), v[4 * j + 0], v[4 * j + 1]);
-          silu2(mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2), v[4 * j + 2], v[4 * j + 3]);
+          silu4<kTsEdgeSilu>(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2),
+                             v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep_first);
         }
       } else {
 #pragma unroll
@@ -445,8 +463,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         for (int j = 0; j < kTsCols / 4; ++j) {
           const float4 pv = __ldg(p4 + j), qv = __ldg(q4 + j), wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
           // silu((P + Q) + radial * w_r), two columns per instruction
-          silu2(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), v[4 * j + 0], v[4 * j + 1]);
-          silu2(mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2), v[4 * j + 2], v[4 * j + 3]);
+          silu4<kTsEdgeSilu>(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2),
+                             v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep_first);
         }
       } else {
 #pragma unroll
@@ -457,6 +475,58 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
       split_hi_lo(v, w);
       publish(a_col + (uint32_t)col0, w);
     };
+
+#if B200MD_TS_PQ_STAGE
+    const int nk0_pq = M / 64;
+    // this thread's private slots: 8 x 16 bytes each, XOR-swizzled so that a warp-wide 128-bit access is conflict-free
+    const uint32_t q_slot = pipe.s_base + L.seg + (uint32_t)(warp - kTsFirstEpiWarp) * kTsSegTileBytes + (uint32_t)lane * 128u;
+    const uint32_t p_slot = pipe.s_base + L.pslot + (uint32_t)(warp - kTsFirstEpiWarp) * kTsSegTileBytes + (uint32_t)lane * 128u;
+    const bool stage_pq = a.n_msg > 0;   // without a hidden message layer segment_add runs inside the first activation
+    auto stage_request = [&](const Edge& ed, int c) {
+      if (ed.valid) {
+        const int col0 = c * 64 + part * kTsCols;
+        const float* pp = a.P + (int64_t)ed.src * M + col0;
+        const float* qq = a.Q + (int64_t)ed.dst * M + col0;
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) {
+          const uint32_t piece = (uint32_t)((j ^ (lane & 7)) << 4);
+          cp_async16(p_slot + piece, pp + 4 * j);
+          cp_async16(q_slot + piece, qq + 4 * j);
+        }
+      }
+      cp_async_commit();
+    };
+    // chunk c of the next tile's first activation from the slots; requests chunk c + 1 once the slots have been read
+    auto first_activation_staged = [&](const Edge& ed, int c, uint32_t a_col) {
+      const int col0 = c * 64 + part * kTsCols;
+      float v[kTsCols];
+      cp_async_wait_all();
+      if (ed.valid) {
+        const uint64_t rad2 = pack2(ed.radial, ed.radial);
+        uint64_t s01[kTsCols / 4], s23[kTsCols / 4];
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) {
+          const uint32_t piece = (uint32_t)((j ^ (lane & 7)) << 4);
+          const float4 pv = lds128_ordered(p_slot + piece), qv = lds128_ordered(q_slot + piece);
+          s01[j] = add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y));
+          s23[j] = add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w));
+        }
+        if (c + 1 < nk0_pq) stage_request(ed, c + 1);
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) {
+          const float4 wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
+          silu4<kTsEdgeSilu>(mul2(fma2(rad2, pack2(wv.x, wv.y), s01[j]), act2), mul2(fma2(rad2, pack2(wv.z, wv.w), s23[j]), act2),
+                             v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep_first);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
+      }
+      uint32_t w[kTsCols];
+      split_hi_lo(v, w);
+      publish(a_col + (uint32_t)col0, w);
+    };
+#endif
 
     const int nk0 = M / 64;
     const int n_last = p.gN[p.n_gemms - 1] / 64;   // chunks of the last accumulator
@@ -490,6 +560,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
           next = load_edge(it + 1);
           prefetch_first(next, 0);
+#if B200MD_TS_PQ_STAGE
+          if (stage_pq) stage_request(next, 0);
+#endif
         }
         int waited = -1;
         auto wait_for_chunk = [&](int c) {
@@ -510,16 +583,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #pragma unroll
           for (int j = 0; j < kTsCols / 4; ++j) {
             const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-            silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1], dep);
-            silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3], dep);
+            silu4<kTsEdgeSilu>(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)),
+                               fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)),
+                               v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep);
             if (j == kTsTokenReleaseAfter) sfu_release(tok_peer, dep);
           }
 #else
 #pragma unroll
           for (int j = 0; j < kTsCols / 4; ++j) {
             const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-            silu2(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
-            silu2(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
+            silu4<kTsEdgeSilu>(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)),
+                               fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)),
+                               v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep_first);
           }
 #endif
           TS_TRACE(5, col0);
@@ -598,6 +673,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #if B200MD_TS_PQ_AHEAD
               first_activation_from(next, c, d_col, ahead);
               if (c + 1 < nk0) load_pq(next, c + 1, ahead);   // used after the next chunk's SiLU and dot product
+#elif B200MD_TS_PQ_STAGE
+              if (stage_pq) first_activation_staged(next, c, d_col);
+              else first_activation_chunk(next, c, d_col);
 #else
               if (c + 1 < nk0) prefetch_first(next, c + 1);
               first_activation_chunk(next, c, d_col);
@@ -609,6 +687,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #if B200MD_TS_PQ_AHEAD
               first_activation_from(next, c, d_col, ahead);
               if (c + 1 < nk0) load_pq(next, c + 1, ahead);
+#elif B200MD_TS_PQ_STAGE
+              if (stage_pq) first_activation_staged(next, c, d_col);
+              else first_activation_chunk(next, c, d_col);
 #else
               if (c + 1 < nk0) prefetch_first(next, c + 1);
               first_activation_chunk(next, c, d_col);

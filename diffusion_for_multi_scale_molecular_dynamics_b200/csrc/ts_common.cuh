@@ -181,6 +181,60 @@ __device__ __forceinline__ void silu2_dep(uint64_t x, float& o0, float& o1, uint
   dep |= __float_as_uint(r0) | __float_as_uint(r1);
   unpack2(mul2(x, pack2(r0, r1)), o0, o1);
 }
+// Shared reciprocals (batch inversion).  With a_i = 1 + 2^(t_i):
+//   pair : r = 1 / (a_0 a_1),  1 / a_0 = r a_1,  1 / a_1 = r a_0                       3 MUFU per 2 elements instead of 4
+//   quad : r = 1 / (a_0 a_1 a_2 a_3),  1 / (a_0 a_1) = r (a_2 a_3), ... then as a pair  5 MUFU per 4 elements instead of 8
+// for a few FMUL / FMNMX more.  The SiLU phases hold the SFU pipe (8.1 cycles per warp instruction, pipe_rates), and
+// under the power cap a MUFU costs more than the multiplies that replace it: A/B on one box, pair: edge launch 19.2 ->
+// 18.9 ms.  t is clamped so that the product of the a_i stays finite (0 x inf would poison the OTHER elements of the
+// group): 2^63 per element for a pair, 2^31 for a quad -- beyond the clamp silu(x) is |x| 2^-31 at most in magnitude, below
+// half an ulp of the unit-scale activations next to it.
+__device__ __forceinline__ void silu2_pair(uint64_t x, float& o0, float& o1, uint32_t& dep) {
+  float t0, t1, e0, e1, a0, a1, r;
+  unpack2(mul2(x, pack2(kTsExpConst, kTsExpConst)), t0, t1);
+  t0 = fminf(t0, 63.0f);
+  t1 = fminf(t1, 63.0f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), a0, a1);
+  const float prod = a0 * a1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(prod));
+  dep |= __float_as_uint(r);
+  unpack2(mul2(x, mul2(pack2(r, r), pack2(a1, a0))), o0, o1);
+}
+__device__ __forceinline__ void silu4_quad(uint64_t x01, uint64_t x23, float& o0, float& o1, float& o2, float& o3, uint32_t& dep) {
+  float t0, t1, t2, t3, e0, e1, e2, e3, a0, a1, a2, a3, p01, p23, r;
+  unpack2(mul2(x01, pack2(kTsExpConst, kTsExpConst)), t0, t1);
+  unpack2(mul2(x23, pack2(kTsExpConst, kTsExpConst)), t2, t3);
+  t0 = fminf(t0, 31.0f); t1 = fminf(t1, 31.0f); t2 = fminf(t2, 31.0f); t3 = fminf(t3, 31.0f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(t2));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(t3));
+  unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), a0, a1);
+  unpack2(add2(pack2(e2, e3), pack2(1.0f, 1.0f)), a2, a3);
+  unpack2(mul2(pack2(a0, a2), pack2(a1, a3)), p01, p23);
+  const float prod = p01 * p23;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(prod));
+  dep |= __float_as_uint(r);
+  float r01, r23;
+  unpack2(mul2(pack2(r, r), pack2(p23, p01)), r01, r23);   // 1 / (a_0 a_1), 1 / (a_2 a_3)
+  unpack2(mul2(x01, mul2(pack2(r01, r01), pack2(a1, a0))), o0, o1);
+  unpack2(mul2(x23, mul2(pack2(r23, r23), pack2(a3, a2))), o2, o3);
+}
+// four elements, MODE 0: one reciprocal each, 1: per pair, 2: per quad
+template <int MODE>
+__device__ __forceinline__ void silu4(uint64_t x01, uint64_t x23, float& o0, float& o1, float& o2, float& o3, uint32_t& dep) {
+  if (MODE == 2) {
+    silu4_quad(x01, x23, o0, o1, o2, o3, dep);
+  } else if (MODE == 1) {
+    silu2_pair(x01, o0, o1, dep);
+    silu2_pair(x23, o2, o3, dep);
+  } else {
+    silu2_dep(x01, o0, o1, dep);
+    silu2_dep(x23, o2, o3, dep);
+  }
+}
 // SFU token between the two epilogue warps that share a scheduler (named barriers of 64 threads, strict alternation):
 // both warps are released by the same accumulator barrier and would otherwise run their SiLU phases (SFU-bound) at the
 // same time and their split / store phases (no SFU) at the same time.
@@ -209,6 +263,19 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+// the same, ordered against the other volatile shared-memory / cp.async statements (slots that are refilled)
+__device__ __forceinline__ float4 lds128_ordered(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+// 16 bytes global -> shared, L2 only (LDGSTS.BYPASS: no register, no L1 line); complete for the issuing thread after
+// cp_async_wait_all
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
