@@ -58,7 +58,16 @@ constexpr int kTsEdgeSilu = B200MD_TS_EDGE_SILU;
 #define B200MD_TS_EDGE_NSPLIT 1
 #endif
 constexpr int kTsEdgeNSplit = B200MD_TS_EDGE_NSPLIT;
-constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes;
+// B200MD_TS_CTA_PAIR = 1: the two CTAs of a cluster work as ONE tcgen05 CTA pair (cta_group::2): the leader (rank 0)
+// issues M = 256 MMAs over both CTAs' rows, every CTA keeps only ITS half of the output columns of a weight part in shared
+// memory (16 KB per stage instead of 32; no multicast), and the tensor core of each SM reads half of B from the peer.
+// The peer's otherwise idle MMA warp forwards its "stage full" / "A chunk ready" barrier completions to the leader.
+#ifndef B200MD_TS_CTA_PAIR
+#define B200MD_TS_CTA_PAIR 1
+#endif
+constexpr bool kTsPair = B200MD_TS_CTA_PAIR != 0;
+static_assert(!kTsPair || (B200MD_TS_CLUSTER == 2 && B200MD_TS_EDGE_NSPLIT == 1), "a CTA pair is a cluster of 2 computing whole-width accumulators");
+constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes / (kTsPair ? 2 : 1);
 // B200MD_TS_PQ_STAGE = 1: the P[src] / Q[dst] rows of the NEXT tile's first activation travel L2 -> shared memory with
 // cp.async (LDGSTS: no registers, no L1 lines held while in flight) into a private 2 x 128-byte slot per epilogue thread,
 // one chunk ahead of their use: chunk 0 is requested when the tile's last layer starts, chunk c + 1 when chunk c has been
@@ -68,6 +77,9 @@ constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes;
 // 19.6 k cycles for the last layer against 8.9 k for a plain one).
 #ifndef B200MD_TS_PQ_STAGE
 #define B200MD_TS_PQ_STAGE 0
+#endif
+#if !defined(B200MD_TS_EDGE_STAGES) && B200MD_TS_CTA_PAIR
+#define B200MD_TS_EDGE_STAGES 10
 #endif
 #ifndef B200MD_TS_EDGE_STAGES
 #define B200MD_TS_EDGE_STAGES (((B200MD_TS_SEG_SMEM ? 11 : 12) * B200MD_TS_EDGE_NSPLIT / 2) - (B200MD_TS_PQ_STAGE ? B200MD_TS_EDGE_NSPLIT : 0))
@@ -161,14 +173,21 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   TsPipe pipe;
   pipe.s_base = smem_u32(smem);
   pipe.bar0 = pipe.s_base + L.bars;
+  const int cta_rank = kTsCluster > 1 ? (int)cluster_ctarank() : 0;
+  const bool pair_leader = kTsPair && cta_rank == 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsEdgeBStages; ++s) { mbar_init(pipe.b_full(s), 1); mbar_init(pipe.b_empty(s), kTsCluster); }
+    // CTA pair: the leader's "full" barriers also count the peer's forwarded completion; a stage is released by ONE
+    // commit (the leader's, multicast) instead of one per CTA
+    for (int s = 0; s < kTsEdgeBStages; ++s) { mbar_init(pipe.b_full(s), pair_leader ? 2 : 1); mbar_init(pipe.b_empty(s), kTsPair ? 1 : kTsCluster); }
     for (int s = 0; s < kTsSlots; ++s)
-      for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), 4);
+      for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), pair_leader ? 5 : 4);
     for (int s = 0; s < 2 * kTsEdgeNSplit; ++s) mbar_init(pipe.acc_full(s / kTsEdgeNSplit, s % kTsEdgeNSplit), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(pipe.s_base + L.tmem_slot, kTmemCols);
+  if (warp == 1) {
+    if (kTsPair) tmem_alloc_pair(pipe.s_base + L.tmem_slot, kTmemCols);
+    else tmem_alloc(pipe.s_base + L.tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   if (kTsCluster > 1) cluster_sync();   // every CTA's barriers exist before a peer's multicast can reach them
@@ -178,7 +197,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   // tile schedule: cluster k of n_clusters takes tiles (i n_clusters + k) kTsCluster + rank, i = 0, 1, ...; every CTA of
   // a cluster runs the same number of iterations (a tile index >= n_tiles is an empty tile)
   const int n_clusters = (int)gridDim.x / kTsCluster, cluster_id = (int)blockIdx.x / kTsCluster;
-  const int cta_rank = kTsCluster > 1 ? (int)cluster_ctarank() : 0;
   const int n_groups = (n_tiles + kTsCluster - 1) / kTsCluster;
   const int n_iterations = n_groups > cluster_id ? (n_groups - cluster_id + n_clusters - 1) / n_clusters : 0;
   const int first_tile = cluster_id * kTsCluster + cta_rank, tile_stride = n_clusters * kTsCluster;
@@ -209,9 +227,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             for (int part = 0; part < 2 * nk; ++part, ++cb) {   // chunk 0 hi, chunk 0 lo, chunk 1 hi, ...
               const uint32_t s = cb % kTsEdgeBStages;
               mbar_wait(pipe.b_empty(s), ((cb / kTsEdgeBStages) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(pipe.b_full(s), bytes);
+              mbar_arrive_expect_tx(pipe.b_full(s), kTsPair ? bytes / 2 : bytes);
               const float* stage_src = src + (int64_t)part * part_floats + (int64_t)h * nh * (kRowBytes / 4);
-              if (kTsCluster > 1) {   // this CTA's slice of the stage, delivered to every CTA of the cluster
+              if (kTsPair) {   // this CTA's half of the output columns, into its own shared memory only
+                const uint32_t half = bytes / 2;
+                bulk_g2s(pipe.s_base + L.b + s * kTsEdgeBStageBytes, stage_src + cta_rank * (half / 4), half, pipe.b_full(s));
+              } else if (kTsCluster > 1) {   // this CTA's slice of the stage, delivered to every CTA of the cluster
                 const uint32_t slice = bytes / kTsCluster;
                 bulk_g2s_multicast(pipe.s_base + L.b + s * kTsEdgeBStageBytes + cta_rank * slice, stage_src + cta_rank * (slice / 4),
                                    slice, pipe.b_full(s), (uint16_t)((1u << kTsCluster) - 1u));
@@ -231,13 +252,38 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     const uint32_t b_ring = pipe.s_base + L.b;
     const bool leader = elect_one();
     uint32_t cb = 0, mca = 0, mgc = 0;
+    if (kTsPair && cta_rank != 0) {
+      // ===== peer of a CTA pair: no MMAs; hand every local "full" completion on to the leader, in the leader's order =====
+      for (int it = 0; it < n_iterations; ++it)
+        for (int g = 0; g < p.n_gemms; ++g) {
+          const int nk = p.gK[g] / 64;
+          for (int c = 0; c < nk; ++c) {
+            const uint32_t s1 = cb % kTsEdgeBStages, s2 = (cb + 1) % kTsEdgeBStages;
+            mbar_wait(pipe.b_full(s1), (cb / kTsEdgeBStages) & 1u);
+            if (leader) mbar_arrive_remote(pipe.b_full(s1), 0u);
+            mbar_wait(pipe.b_full(s2), ((cb + 1) / kTsEdgeBStages) & 1u);
+            if (leader) mbar_arrive_remote(pipe.b_full(s2), 0u);
+            const uint32_t chunk = mca + (uint32_t)c;
+#pragma unroll
+            for (int j = 0; j < kTsParts; ++j) {
+              mbar_wait(pipe.a_full(chunk % kTsSlots, j), (chunk / kTsSlots) & 1u);
+              tc_fence_after();
+              tc_fence_before();
+              if (leader) mbar_arrive_remote(pipe.a_full(chunk % kTsSlots, j), 0u);
+            }
+            __syncwarp();
+            cb += 2;
+          }
+          mca += nk;
+        }
+    } else
     for (int it = 0; it < n_iterations; ++it)
       for (int g = 0; g < p.n_gemms; ++g, ++mgc) {
 #ifdef B200MD_TS_TRACE
         trace_on = (blockIdx.x == 0 && lane == 0 && it >= 3 && it < 5);
 #endif
         const int nk = p.gK[g] / 64, nh = p.gN[g] / kTsEdgeNSplit;
-        const uint32_t idesc = make_idesc(nh, 0u);
+        const uint32_t idesc = kTsPair ? make_idesc_pair(nh, 0u) : make_idesc(nh, 0u);
         const uint32_t d_col = (mgc & 1u) * kMaxN, a_col = d_col ^ kMaxN;
         for (int h = 0; h < kTsEdgeNSplit; ++h) {
           const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(h * nh);
@@ -257,13 +303,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               }
               tc_fence_after();
               if (leader) {
-                umma_f16_ts(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);   // A_1 B_1
-                umma_f16_ts(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescA2, 1u);   // A_2 B_1 (A_2 is stored negated)
-                umma_f16_ts(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);             // A_1 B_2
+                umma_f16_ts<kTsPair>(d_tmem, a_chunk + j * 16, bd1 + 2 * j, idesc, (c | j) != 0);   // A_1 B_1
+                umma_f16_ts<kTsPair>(d_tmem, a_chunk + j * 16 + 8, bd1 + 2 * j, idesc | kIdescA2, 1u);   // A_2 B_1 (A_2 is stored negated)
+                umma_f16_ts<kTsPair>(d_tmem, a_chunk + j * 16, bd2 + 2 * j, idesc, 1u);             // A_1 B_2
               }
             }
             if (leader) {   // a stage is free when EVERY CTA of the cluster has consumed it: the peers write into it too
-              if (kTsCluster > 1) {
+              if (kTsPair) {
+                umma_commit_pair(pipe.b_empty(s1), 3u);
+                umma_commit_pair(pipe.b_empty(s2), 3u);
+              } else if (kTsCluster > 1) {
                 umma_commit_multicast(pipe.b_empty(s1), (uint16_t)((1u << kTsCluster) - 1u));
                 umma_commit_multicast(pipe.b_empty(s2), (uint16_t)((1u << kTsCluster) - 1u));
               } else {
@@ -274,7 +323,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
             __syncwarp();
             cb += 2;
           }
-          if (leader) umma_commit(pipe.acc_full(mgc & 1u, h));
+          if (leader) {
+            if (kTsPair) umma_commit_pair(pipe.acc_full(mgc & 1u, h), 3u);   // both CTAs' epilogues
+            else umma_commit(pipe.acc_full(mgc & 1u, h));
+          }
           __syncwarp();
           TS_TRACE(120 + h, g);
         }
@@ -734,6 +786,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   tc_fence_after();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(pipe.tmem_base, kTmemCols);
+    if (kTsPair) tmem_dealloc_pair(pipe.tmem_base, kTmemCols);
+    else tmem_dealloc(pipe.tmem_base, kTmemCols);
   }
 }

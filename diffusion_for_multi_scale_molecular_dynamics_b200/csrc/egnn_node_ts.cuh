@@ -20,6 +20,9 @@
 
 #include "ts_common.cuh"
 
+#ifndef B200MD_NODE_TS_EXACT_DIV
+#define B200MD_NODE_TS_EXACT_DIV 0
+#endif
 #ifndef B200MD_NODE_TS_PIPELINED
 #define B200MD_NODE_TS_PIPELINED 1
 #endif
@@ -323,6 +326,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       const int64_t node = (int64_t)tile * kTileM + row;
       const bool valid = node < a.n_nodes;
       const float degf = valid ? fmaxf((float)a.deg[node], 1.0f) : 1.0f;
+      // mean = sum x (1 / max(deg, 1)) with the correctly rounded reciprocal: at most 1 ulp from the reference's division
+      // (models/egnn_utils.py:53-70), and 32 IEEE divisions per thread and chunk were 2.4 k of the 4 k cycles each chunk
+      // of the tile's first A operand took (cycle trace)
+      const float inv_deg = __frcp_rn(degf);
       // ---- warp-cooperative row access through the staging tile (see kNodeStageBytes) ----
       const int64_t warp_row0 = (int64_t)tile * kTileM + q * 32;   // node of lane 0's row
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.n_nodes - warp_row0));   // warp-uniform
@@ -475,14 +482,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         for (int c = 0; c < M / 64; ++c) {
           const int col0 = c * 64 + part * kTsCols;
           float v[kTsCols];
+          NODE_TRACE(22, c);
           rows_collect(ahead, v);   // the loads have returned here: the reset below may follow (a store issued right
                                     // behind loads of the same addresses doubles the time of the whole kernel, measured)
+          NODE_TRACE(23, c);
           if (c + 1 < M / 64) rows_request(a.agg, M, col0 + 64, ahead);
           if (a.message_mean) {
 #pragma unroll
-            for (int j = 0; j < kTsCols; ++j) v[j] = v[j] / degf;
+            for (int j = 0; j < kTsCols; ++j) v[j] = B200MD_NODE_TS_EXACT_DIV ? v[j] / degf : v[j] * inv_deg;
           }
+          NODE_TRACE(24, c);
           rows_zero(a.agg, M, col0);
+          NODE_TRACE(25, c);
           publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
           NODE_TRACE(21, c);
         }
@@ -545,7 +556,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             } else {
 #pragma unroll
               float side[kTsCols];
+              NODE_TRACE(26, g * 16 + c);
               rows_collect(side_tile, side);
+              NODE_TRACE(27, g * 16 + c);
               if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);   // U of the next chunk
 #pragma unroll
               for (int j = 0; j < kTsCols / 2; ++j)
@@ -585,9 +598,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           uint32_t r[kTsCols];
           float v[kTsCols];
           tmem_load_cols(lane_taddr + d_col + col0, r);
+          NODE_TRACE(28, g * 16 + c);
           float u[kTsCols];
           if (side_rows != nullptr) {   // warp-uniform
             rows_collect(side_tile, u);
+            NODE_TRACE(29, g * 16 + c);
             if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);
           }
           if (G.kind == kNodeChain) {
@@ -639,6 +654,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               for (int j = 0; j < kTsCols; ++j) checksum += v[j];
             }
           }
+          NODE_TRACE(31, g * 16 + c);
           if (becomes_a) publish(d_col + (uint32_t)col0, v, G.kind == kNodeChainLast ? kF16ActScale : 1.0f);
           NODE_TRACE(30, g * 16 + c);
           if (G.signal_d_free) {   // every column group that ends inside this chunk is drained now

@@ -48,10 +48,54 @@ __device__ __forceinline__ int ts_last_group_of_chunk(int c, int nh) {
   return need;
 }
 
+// ---- CTA pair (tcgen05 cta_group::2) ----
+// M = 256 over the two CTAs of the pair (128 rows each), N = n in all (each CTA holds n / 2 rows of B)
+__device__ __forceinline__ uint32_t make_idesc_pair(int n, uint32_t format) {
+  return (1u << 4) | (format << 7) | (format << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * kTileM) >> 4) << 24);
+}
+// executed by the same warp of BOTH CTAs (same slot address)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive on the barrier at this CTA-relative address in every CTA of `cta_mask` when the pair's MMAs issued so far are complete
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+// arrive on the barrier at this CTA-relative address in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]^T
 // `b_desc_lo`: low word of the K-major SWIZZLE_128B descriptor (desc_lo_sw128); the high word is a constant.
+template <bool PAIR = false>
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t idesc,
                                             uint32_t accumulate) {
+  if (PAIR) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 bd;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_desc_lo), "r"(idesc), "r"(accumulate), "n"(kDescHiSw128)
+        : "memory");
+    return;
+  }
   asm volatile(
       "{\n"
       ".reg .pred p;\n"

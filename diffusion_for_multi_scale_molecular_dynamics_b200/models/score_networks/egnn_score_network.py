@@ -139,8 +139,8 @@ class EGNNScoreNetwork(ScoreNetwork):
         return {_cabi.IMPL_FFMA: "egnn_edge_kernel (fp32 FFMA tiles)",
                 _cabi.IMPL_TCGEN05: "egnn_edge_tc_kernel (tcgen05 3xTF32, fp32 accumulate in TMEM)",
                 _cabi.IMPL_TCGEN05_F16X3: "egnn_edge_tc_kernel (tcgen05 3xFP16, fp32 accumulate in TMEM)",
-                _cabi.IMPL_TCGEN05_F16X3_TS: "egnn_edge_ts_kernel (tcgen05 3xFP16, A operand and fp32 accumulators "
-                                             "in TMEM)"}.get(
+                _cabi.IMPL_TCGEN05_F16X3_TS: "egnn_edge_ts_kernel (tcgen05 cta_group::2 3xFP16, A operand and fp32 "
+                                             "accumulators in TMEM)"}.get(
                     resolved, f"unsupported ({resolved})")
 
     # ---- reference helpers kept for API compatibility ----------------------------------------------------
