@@ -276,14 +276,19 @@ __global__ void pc_lattice_update_kernel(const float* l, const float* __restrict
 // -------------------------------------------------------------------------------------------------
 constexpr int kMaxClasses = 32;
 
+// CT > 0: the number of classes at compile time (every per-atom array in registers, loops unrolled); CT = 0: run time
+// (the arrays are indexed dynamically and live in local memory: 3.4 x slower at C = 3).  Same operations in the same order.
+template <int CT>
 __global__ void atom_types_update_kernel(const float* __restrict__ logits, const int64_t* a_in,
                                          const float* __restrict__ q, const float* __restrict__ qbar,
                                          const float* __restrict__ qbar_tm1,
                                          const float* __restrict__ gumbel, const float* __restrict__ binary,
-                                         int32_t flags, float eps, int32_t n_atoms, int32_t C,
+                                         int32_t flags, float eps, int32_t n_atoms, int32_t C_runtime,
                                          uint64_t seed, uint32_t step_id, uint64_t sample_offset,
                                          int64_t* a_out, float* __restrict__ probs_out,
                                          int32_t* __restrict__ status, const PcStepScalars* cur, int phase) {
+  const int C = CT > 0 ? CT : C_runtime;
+  constexpr int kArr = CT > 0 ? CT : kMaxClasses;
   if (cur != nullptr) {   // graph replay: flags, table rows and the draw key of THIS step (sampler.cuh)
     const bool predictor = phase == 0;
     flags = predictor ? cur->atom_flags_pred : cur->atom_flags_corr;
@@ -323,32 +328,32 @@ __global__ void atom_types_update_kernel(const float* __restrict__ logits, const
   for (int n = threadIdx.x; n < n_atoms; n += blockDim.x) {
     const int64_t node = smp * n_atoms + n;
     const int at = (int)a_row[n];
-    float p0[kMaxClasses];
+    float p0[kArr];
     // softmax -> clip -> renormalise   utils/d3pm_utils.py:140-149
     float mx = -CUDART_INF_F;
-    for (int c = 0; c < C; ++c) { p0[c] = logits[node * C + c]; mx = fmaxf(mx, p0[c]); }
+    _Pragma("unroll") for (int c = 0; c < C; ++c) { p0[c] = logits[node * C + c]; mx = fmaxf(mx, p0[c]); }
     float sum = 0.f;
-    for (int c = 0; c < C; ++c) { p0[c] = expf(p0[c] - mx); sum += p0[c]; }
+    _Pragma("unroll") for (int c = 0; c < C; ++c) { p0[c] = expf(p0[c] - mx); sum += p0[c]; }
     float check = 0.f;
-    for (int c = 0; c < C; ++c) { p0[c] = p0[c] / sum; check += p0[c]; }
+    _Pragma("unroll") for (int c = 0; c < C; ++c) { p0[c] = p0[c] / sum; check += p0[c]; }
     if (!(fabsf(check - 1.0f) <= 1e-5f + 1.3e-6f)) local_status |= B200MD_STATUS_BAD_LOGITS;
     float csum = 0.f;
-    for (int c = 0; c < C; ++c) { p0[c] = fmaxf(p0[c], eps); csum += p0[c]; }
-    for (int c = 0; c < C; ++c) p0[c] = p0[c] / csum;
+    _Pragma("unroll") for (int c = 0; c < C; ++c) { p0[c] = fmaxf(p0[c], eps); csum += p0[c]; }
+    _Pragma("unroll") for (int c = 0; c < C; ++c) p0[c] = p0[c] / csum;
     // p(a_{t-1} | a_t)   utils/d3pm_utils.py:102-124
     float den = 0.f;
-    for (int j = 0; j < C; ++j) den += p0[j] * s_q[C * C + j * C + at];
-    float prob[kMaxClasses];
-    for (int i = 0; i < C; ++i) {
+    _Pragma("unroll") for (int j = 0; j < C; ++j) den += p0[j] * s_q[C * C + j * C + at];
+    float prob[kArr];
+    _Pragma("unroll") for (int i = 0; i < C; ++i) {
       float num1 = 0.f;
-      for (int j = 0; j < C; ++j) num1 += p0[j] * s_q[2 * C * C + j * C + i];
+      _Pragma("unroll") for (int j = 0; j < C; ++j) num1 += p0[j] * s_q[2 * C * C + j * C + i];
       float num2 = s_q[i * C + at];
       prob[i] = (num1 * num2) / den;
     }
     // Gumbel noise
-    float gum[kMaxClasses];
+    float gum[kArr];
     if (gumbel != nullptr) {
-      for (int c = 0; c < C; ++c) gum[c] = gumbel[node * C + c];
+      _Pragma("unroll") for (int c = 0; c < C; ++c) gum[c] = gumbel[node * C + c];
     } else {
       const int nblk = (C + 3) >> 2;
       for (int b = 0; b < nblk; ++b) {
@@ -371,13 +376,13 @@ __global__ void atom_types_update_kernel(const float* __restrict__ logits, const
       const bool do_greedy = (!all_masked) && (bin > prob[mask_class]) && (at == mask_class);
       if (do_greedy) prob[mask_class] = 0.f;
       if (!all_masked)
-        for (int c = 0; c < C; ++c) gum[c] = 0.f;
+        _Pragma("unroll") for (int c = 0; c < C; ++c) gum[c] = 0.f;
     }
     if (probs_out != nullptr)
-      for (int c = 0; c < C; ++c) probs_out[node * C + c] = prob[c];
+      _Pragma("unroll") for (int c = 0; c < C; ++c) probs_out[node * C + c] = prob[c];
     float best = -CUDART_INF_F;
     int best_c = 0;
-    for (int c = 0; c < C; ++c) {
+    _Pragma("unroll") for (int c = 0; c < C; ++c) {
       float v = logf(prob[c] + eps) + gum[c];
       if (v > best || c == 0) { best = v; best_c = c; }  // first maximum wins (torch.max)
     }
@@ -560,6 +565,9 @@ __device__ __forceinline__ float wrapped_gaussian_score_value_f32(float u, float
       const float kk = (float)k;
       // u < 1/2: k^2 + 2 u k (:271-273); else (k^2 - 1) + 2 u (k + 1) (:294-297)
       const float q = small_u ? fmaf(two_u, kk, kk * kk) : fmaf(two_u, kk + 1.0f, kk * kk - 1.0f);
+      // a term below exp(-104) is exactly 0 in fp32 (ex2.approx.ftz): when that holds for every lane of the warp -- the
+      // usual case, sigma being one value per sample: for sigma < 0.1 only k = -1, 0, 1 survive -- the SFU work is skipped
+      if (__all_sync(__activemask(), c * q < -104.0f)) continue;
       const float e = __expf(c * q);
       num = fmaf(kk, e, num);
       den += e;
@@ -702,9 +710,13 @@ int atom_types_update_impl(const float* logits, const int64_t* atom_types, const
   if (threads > 256) threads = 256;
   size_t smem = (size_t)3 * n_classes * n_classes * sizeof(float) + (size_t)n_atoms * 8;
   if (smem > 200 * 1024) return B200MD_ERR_UNSUPPORTED;
+  auto kernel = atom_types_update_kernel<0>;
+  if (n_classes == 2) kernel = atom_types_update_kernel<2>;        // Si (+ MASK)
+  else if (n_classes == 3) kernel = atom_types_update_kernel<3>;   // SiGe (+ MASK)
+  else if (n_classes == 4) kernel = atom_types_update_kernel<4>;
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(atom_types_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); atom_types_update_kernel<<<(unsigned)n_samples, threads, smem, st>>>(
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  { ProfileScope ps__(B200MD_KERNEL_UPDATE, st); kernel<<<(unsigned)n_samples, threads, smem, st>>>(
       logits, atom_types, q, q_bar, q_bar_tm1, gumbel, binary, flags, small_epsilon, n_atoms, n_classes,
       seed, step_id, sample_offset, atom_types_out, probs_out, status, cur, phase); }
   B200MD_CHECK_LAUNCH();

@@ -73,6 +73,12 @@ wg_out = torch.empty_like(u)
 ms = timed(lambda: _cabi.check(lib.b200md_wrapped_gaussian_score_f32(_cabi.ptr(u), _cabi.ptr(sig), u.numel(), 4,
                                                                      _cabi.ptr(wg_out), stream)))
 report("wrapped_gaussian_score_kernel<f32>, kmax 4", ms, 12 * u.numel(), f"{u.numel()} elements, sigma in (0.001, 0.5)")
+# the shape the reference calls it with: one sigma per SAMPLE broadcast over its atoms x 3 coordinates (64 atoms: runs of 192)
+sig = (torch.rand(u.numel() // 192, 1, device=dev) * 0.5 + 0.001).expand(-1, 192).reshape(-1).contiguous()
+ms = timed(lambda: _cabi.check(lib.b200md_wrapped_gaussian_score_f32(_cabi.ptr(u), _cabi.ptr(sig), u.numel(), 4,
+                                                                     _cabi.ptr(wg_out), stream)))
+report("wrapped_gaussian_score_kernel<f32>, kmax 4, sigma per sample", ms, 12 * u.numel(),
+       f"{u.numel()} elements, sigma in (0.001, 0.5) constant over runs of 192 elements (one 64-atom sample): one branch per warp")
 del u, sig, wg_out, x, s, out
 # ---- atom-type update: 16 + 4C B / atom ------------------------------------------------------------------------------
 B, N, C = 32768, 512, 3
