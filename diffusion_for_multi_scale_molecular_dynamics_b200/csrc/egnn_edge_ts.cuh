@@ -79,7 +79,10 @@ constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes / (kTsPai
 #define B200MD_TS_PQ_STAGE 0
 #endif
 #if !defined(B200MD_TS_EDGE_STAGES) && B200MD_TS_CTA_PAIR
-#define B200MD_TS_EDGE_STAGES 10
+#define B200MD_TS_EDGE_STAGES (B200MD_TS_PQ_STAGE ? 8 : 10)
+#endif
+#ifndef B200MD_TS_NEXT_EDGE_AHEAD
+#define B200MD_TS_NEXT_EDGE_AHEAD 0
 #endif
 #ifndef B200MD_TS_EDGE_STAGES
 #define B200MD_TS_EDGE_STAGES (((B200MD_TS_SEG_SMEM ? 11 : 12) * B200MD_TS_EDGE_NSPLIT / 2) - (B200MD_TS_PQ_STAGE ? B200MD_TS_EDGE_NSPLIT : 0))
@@ -507,13 +510,27 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     auto first_activation_chunk = [&](const Edge& ed, int c, uint32_t a_col) {
       const int col0 = c * 64 + part * kTsCols;
       float v[kTsCols];
+      TS_TRACE(20, c);
       if (ed.valid) {
         const uint64_t rad2 = pack2(ed.radial, ed.radial);
         const float4* p4 = reinterpret_cast<const float4*>(a.P + (int64_t)ed.src * M + col0);
         const float4* q4 = reinterpret_cast<const float4*>(a.Q + (int64_t)ed.dst * M + col0);
+#ifdef B200MD_TS_TRACE
+        float4 pvs[kTsCols / 4], qvs[kTsCols / 4];
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) { pvs[j] = __ldg(p4 + j); qvs[j] = __ldg(q4 + j); }
+        float probe = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) probe += pvs[j].x + qvs[j].w;
+        TS_TRACE(24, __float_as_uint(probe) & 1u);
+#endif
 #pragma unroll
         for (int j = 0; j < kTsCols / 4; ++j) {
+#ifdef B200MD_TS_TRACE
+          const float4 pv = pvs[j], qv = qvs[j], wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
+#else
           const float4 pv = __ldg(p4 + j), qv = __ldg(q4 + j), wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
+#endif
           // silu((P + Q) + radial * w_r), two columns per instruction
           silu4<kTsEdgeSilu>(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2),
                              v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep_first);
@@ -523,8 +540,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
       }
       if (a.n_msg == 0) segment_add(ed, v, a.agg, M, col0);  // no hidden layer: this IS the message
+      TS_TRACE(21, __float_as_uint(v[0] + v[kTsCols - 1]) & 1u);
       uint32_t w[kTsCols];
       split_hi_lo(v, w);
+      TS_TRACE(22, (w[0] ^ w[kTsCols - 1]) & 1u);
       publish(a_col + (uint32_t)col0, w);
     };
 
@@ -592,6 +611,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         first_activation_chunk(cur, c, a_col);
       }
     }
+    const int g_next_edge = p.n_gemms - 1 - B200MD_TS_NEXT_EDGE_AHEAD > 0 ? p.n_gemms - 1 - B200MD_TS_NEXT_EDGE_AHEAD : 0;
     for (int it = 0; it < n_iterations; ++it) {
 #ifdef B200MD_TS_TRACE
       trace_on = (blockIdx.x == 0 && lane == 0 && q == 0 && it >= 3 && it < 5);
@@ -609,13 +629,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
         // accumulator = 2^s (weights) x kF16ActScale (A operand) x product; kF16ActScale x pre-activation = acc 2^-s + bias'
         const float unscale = lds32(pipe.s_base + L.scale + (uint32_t)g * 4u);
         const uint64_t unscale2 = pack2(unscale, unscale);
-        if (is_last && has_next) {   // the next tile's edge and the first lines of its P / Q rows, while the last MMAs run
+        // the next tile's edge (indices, radial: two dependent round trips) is requested B200MD_TS_NEXT_EDGE_AHEAD layers
+        // before the last one, so that it is in registers when the staged copies of its P / Q rows are issued
+        if (g == g_next_edge && has_next) {
           next = load_edge(it + 1);
           prefetch_first(next, 0);
-#if B200MD_TS_PQ_STAGE
-          if (stage_pq) stage_request(next, 0);
-#endif
         }
+#if B200MD_TS_PQ_STAGE
+        if (is_last && has_next && stage_pq) stage_request(next, 0);
+#endif
         int waited = -1;
         auto wait_for_chunk = [&](int c) {
           const int need = ts_last_group_of_chunk<kTsEdgeNSplit>(c, nh);
@@ -719,6 +741,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               dot = fmaf(v[4 * j + 2], w.z, dot);
               dot = fmaf(v[4 * j + 3], w.w, dot);
             }
+            TS_TRACE(23, __float_as_uint(dot) & 1u);
             // these accumulator columns are free now: the next tile's first activation goes there IN PLACE, so its
             // first GEMM starts while this tile is being finished
             if (has_next && c < nk0) {
