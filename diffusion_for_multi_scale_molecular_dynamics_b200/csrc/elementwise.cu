@@ -565,9 +565,6 @@ __device__ __forceinline__ float wrapped_gaussian_score_value_f32(float u, float
       const float kk = (float)k;
       // u < 1/2: k^2 + 2 u k (:271-273); else (k^2 - 1) + 2 u (k + 1) (:294-297)
       const float q = small_u ? fmaf(two_u, kk, kk * kk) : fmaf(two_u, kk + 1.0f, kk * kk - 1.0f);
-      // a term below exp(-104) is exactly 0 in fp32 (ex2.approx.ftz): when that holds for every lane of the warp -- the
-      // usual case, sigma being one value per sample: for sigma < 0.1 only k = -1, 0, 1 survive -- the SFU work is skipped
-      if (__all_sync(__activemask(), c * q < -104.0f)) continue;
       const float e = __expf(c * q);
       num = fmaf(kk, e, num);
       den += e;
