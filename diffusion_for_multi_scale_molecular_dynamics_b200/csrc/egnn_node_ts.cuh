@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         for (int p = 0; p < 8; ++p)
           sts128(stage + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4), v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
         __syncwarp();
+        NODE_TRACE(35, col);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int R = 4 * i + crow;
@@ -604,6 +605,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             rows_collect(side_tile, u);
             NODE_TRACE(29, g * 16 + c);
             if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);
+            NODE_TRACE(32, g * 16 + c);
           }
           if (G.kind == kNodeChain) {
 #pragma unroll
@@ -631,7 +633,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 #pragma unroll
                 for (int j = 0; j < kTsCols; ++j) v[j] = u[j] + v[j];
               }
+              NODE_TRACE(33, (g * 16 + c) | ((__float_as_uint(v[0] + v[31]) & 1u) << 20));
               rows_store(a.h, H, col0, v);
+              NODE_TRACE(34, g * 16 + c);
               if (a.do_readout) {   // logits = W_c h + b_c (egnn.py:379): partial dot products while h' is in registers
 #pragma unroll
                 for (int cl = 0; cl < kNodeMaxClasses; ++cl)
@@ -647,7 +651,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                   }
               }
             } else {
+              NODE_TRACE(33, (g * 16 + c) | ((__float_as_uint(v[0] + v[31]) & 1u) << 20));
               rows_store(G.out, G.N, col0, v);
+              NODE_TRACE(34, g * 16 + c);
             }
             if (valid) {
 #pragma unroll

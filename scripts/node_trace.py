@@ -40,7 +40,7 @@ net(batch, conditional=False)
 n = lib.b200md_debug_node_trace(buf, records)
 rec = np.frombuffer(buf, dtype=np.uint32).reshape(-1, 4)[:n]
 rec = rec[rec[:, 0] != 0]
-names = {1: "acc_wait", 2: "acc_ready", 5: "silu_done", 6: "published", 20: "tile_begin", 21: "first_A_published", 22: "agg_collect", 23: "agg_here", 24: "agg_divided", 25: "agg_zeroed", 26: "side_collect", 27: "side_here", 28: "acc_loaded", 29: "side_here", 31: "stored", 30: "chunk_done",
+names = {1: "acc_wait", 2: "acc_ready", 5: "silu_done", 6: "published", 20: "tile_begin", 21: "first_A_published", 22: "agg_collect", 23: "agg_here", 24: "agg_divided", 25: "agg_zeroed", 26: "side_collect", 27: "side_here", 28: "acc_loaded", 29: "side_here", 31: "stored", 32: "side_requested", 33: "computed", 34: "rows_stored", 35: "staged", 30: "chunk_done",
          100: "A_wait_p0", 102: "A_wait_p1", 110: "A_got_p0", 112: "A_got_p1", 120: "grp0_committed", 121: "grp1_committed",
          130: "dfree_wait0", 131: "dfree_wait1", 140: "dfree_got0", 141: "dfree_got1"}
 t0 = int(rec[:, 3].astype(np.int64).min())
@@ -48,5 +48,5 @@ events = sorted((int((int(c) - t0) & 0xffffffff), int(w), int(e), int(arg)) for 
 first_epi = min(w for _, w, _, _ in events if w != 1)
 for t, w, e, arg in events:
     col = 0 if w == 1 else (40 if w == first_epi else 80)
-    label = f"{names.get(e, e)} g{arg // 16}c{arg % 16}" if e not in (20, 21, 22, 23, 24, 25, 120, 121, 130, 131, 140, 141) else f"{names.get(e, e)} {arg}"
+    label = f"{names.get(e, e)} g{(arg & 0xfffff) // 16}c{arg % 16}" if e not in (20, 21, 22, 23, 24, 25, 120, 121, 130, 131, 140, 141) else f"{names.get(e, e)} {arg}"
     print(f"{t:9d} " + " " * col + label)
