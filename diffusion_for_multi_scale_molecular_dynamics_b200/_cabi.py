@@ -146,6 +146,8 @@ SIGNATURES = {
     "b200md_radius_graph_count": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "b200md_radius_graph_fill": (
         c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, c_int32, _P, c_int64, _P, _P, _P, _P, _P]),
+    "b200md_radius_graph_count_masked": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, _P, _P, _P, _P, _P]),
+    "b200md_radius_graph_fill_from_mask": (c_int32, [_P, c_int64, c_int32, _P, c_int64, _P, _P, _P, _P]),
     "b200md_pair_distances_count": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, _P, _P, _P]),
     "b200md_pair_distances_fill": (c_int32, [_P, _P, c_int32, c_float, c_int64, c_int32, _P, _P, _P]),
     "b200md_repulsive_pseudo_force": (c_int32, [_P, _P, c_float, c_float, c_float, c_int64, c_int32, _P, _P, _P, _P]),

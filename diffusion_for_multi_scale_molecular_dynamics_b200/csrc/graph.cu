@@ -21,7 +21,7 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
                                           float rc2, int32_t N, int32_t mode,
                                           int32_t* __restrict__ counts,
                                           int64_t* __restrict__ edges_per_structure,
-                                          int32_t* __restrict__ status) {
+                                          int32_t* __restrict__ status, uint32_t* __restrict__ hit_mask) {
   extern __shared__ float smem[];
   float* px = smem; float* py = px + N; float* pz = py + N;
   float* lat = pz + N;  // [27][3]
@@ -47,7 +47,10 @@ __global__ void radius_graph_count_kernel(const float* __restrict__ positions,
         const int j = j0 + lane;
         bool hit = false;
         if (j < N) hit = first_image_hit_among(xi, yi, zi, px[j], py[j], pz[j], lat, rc2, candidates) >= 0;
-        deg += __popc(__ballot_sync(0xffffffffu, hit));
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        deg += __popc(ballot);
+        // the hit bit row of (b, i): the fill expands it without sweeping again (b200md_radius_graph_fill_from_mask)
+        if (hit_mask != nullptr && lane == 0) hit_mask[(b * N + i) * (int64_t)((N + 31) >> 5) + (j0 >> 5)] = ballot;
       }
       if (lane == 0) { counts[b * N + i] = deg; local += deg; }
     }
@@ -150,6 +153,33 @@ __global__ void radius_graph_fill_kernel(const float* __restrict__ positions, co
       }
       __syncwarp();
     }
+  }
+}
+
+// Unique-pair edges from the hit bit rows the count pass left behind: one warp per source atom, no positions, no second
+// N^2 sweep.  Ascending destination inside a row, rows in (structure, source) order: the torch.unique(dim=1) order.
+__global__ void radius_graph_fill_from_mask_kernel(const uint32_t* __restrict__ hit_mask, int64_t n_rows, int32_t N,
+                                                   const int64_t* __restrict__ offsets, int64_t node_offset,
+                                                   int64_t* __restrict__ src_out, int64_t* __restrict__ dst_out,
+                                                   int64_t* __restrict__ edge_batch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int words = (N + 31) >> 5;
+  const int64_t b = row / N;
+  const int i = (int)(row - b * N);
+  const int64_t base_node = b * node_offset;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int64_t pos = offsets[row];
+  for (int w = 0; w < words; ++w) {
+    const unsigned bits = hit_mask[row * words + w];   // warp-uniform
+    if (bits >> lane & 1u) {
+      const int64_t e = pos + __popc(bits & lt_mask);
+      src_out[e] = base_node + i;
+      dst_out[e] = base_node + (w * 32 + lane);
+      if (edge_batch) edge_batch[e] = b;
+    }
+    pos += __popc(bits);
   }
 }
 
@@ -344,10 +374,10 @@ using namespace b200md;
 
 extern "C" {
 
-int b200md_radius_graph_count(const float* positions, const float* cell, int32_t positions_are_relative,
-                              float radial_cutoff, int64_t n_samples, int32_t n_atoms, int32_t mode,
-                              int32_t* counts, int64_t* edges_per_structure, int32_t* status,
-                              b200md_stream_t stream) {
+static int radius_graph_count_impl(const float* positions, const float* cell, int32_t positions_are_relative,
+                                   float radial_cutoff, int64_t n_samples, int32_t n_atoms, int32_t mode,
+                                   int32_t* counts, int64_t* edges_per_structure, int32_t* status,
+                                   uint32_t* hit_mask, b200md_stream_t stream) {
   if (!positions || !cell || !counts || !edges_per_structure || !status || n_samples < 0 || n_atoms <= 0 ||
       !(radial_cutoff > 0.f) || (mode != B200MD_GRAPH_UNIQUE_PAIRS && mode != B200MD_GRAPH_PER_IMAGE))
     return B200MD_ERR_INVALID_ARGUMENT;
@@ -359,7 +389,38 @@ int b200md_radius_graph_count(const float* positions, const float* cell, int32_t
     cudaFuncSetAttribute(radius_graph_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream)); radius_graph_count_kernel<<<(unsigned)n_samples, threads, smem, as_stream(stream)>>>(
       positions, cell, positions_are_relative, radial_cutoff, radial_cutoff * radial_cutoff, n_atoms, mode,
-      counts, edges_per_structure, status); }
+      counts, edges_per_structure, status, hit_mask); }
+  B200MD_CHECK_LAUNCH();
+  return B200MD_OK;
+}
+
+int b200md_radius_graph_count(const float* positions, const float* cell, int32_t positions_are_relative,
+                              float radial_cutoff, int64_t n_samples, int32_t n_atoms, int32_t mode,
+                              int32_t* counts, int64_t* edges_per_structure, int32_t* status,
+                              b200md_stream_t stream) {
+  return radius_graph_count_impl(positions, cell, positions_are_relative, radial_cutoff, n_samples, n_atoms, mode, counts,
+                                 edges_per_structure, status, nullptr, stream);
+}
+
+int b200md_radius_graph_count_masked(const float* positions, const float* cell, int32_t positions_are_relative,
+                                     float radial_cutoff, int64_t n_samples, int32_t n_atoms, int32_t* counts,
+                                     int64_t* edges_per_structure, int32_t* status, uint32_t* hit_mask,
+                                     b200md_stream_t stream) {
+  if (!hit_mask) return B200MD_ERR_INVALID_ARGUMENT;
+  return radius_graph_count_impl(positions, cell, positions_are_relative, radial_cutoff, n_samples, n_atoms,
+                                 B200MD_GRAPH_UNIQUE_PAIRS, counts, edges_per_structure, status, hit_mask, stream);
+}
+
+int b200md_radius_graph_fill_from_mask(const uint32_t* hit_mask, int64_t n_samples, int32_t n_atoms,
+                                       const int64_t* offsets, int64_t node_index_offset, int64_t* src_out,
+                                       int64_t* dst_out, int64_t* edge_batch, b200md_stream_t stream) {
+  if (!hit_mask || !offsets || !src_out || !dst_out || n_samples < 0 || n_atoms <= 0) return B200MD_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0) return B200MD_OK;
+  const int64_t n_rows = n_samples * n_atoms;
+  const int warps_per_block = 8;
+  { ProfileScope ps__(B200MD_KERNEL_GRAPH, as_stream(stream));
+    radius_graph_fill_from_mask_kernel<<<(unsigned)((n_rows + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, as_stream(stream)>>>(
+        hit_mask, n_rows, n_atoms, offsets, node_index_offset, src_out, dst_out, edge_batch); }
   B200MD_CHECK_LAUNCH();
   return B200MD_OK;
 }

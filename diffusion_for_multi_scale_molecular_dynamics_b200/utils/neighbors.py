@@ -42,9 +42,18 @@ def _radius_graph(
     per_structure = torch.empty(batch_size, dtype=torch.int64, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     stream = _cabi.stream_ptr(device)
-    _cabi.check(lib.b200md_radius_graph_count(
-        _cabi.ptr(pos), _cabi.ptr(basis), int(positions_are_relative), float(radial_cutoff), batch_size, natom, mode,
-        _cabi.ptr(counts), _cabi.ptr(per_structure), _cabi.ptr(status), stream))
+    # unique pairs without shifts: ONE sweep -- the count pass keeps the hit bit row of every source atom and the fill
+    # expands those rows; the other forms need the image (shifts) or the distances (per-image order) again and sweep twice
+    one_sweep = mode == _cabi.GRAPH_UNIQUE_PAIRS and not want_shifts
+    if one_sweep:
+        hit_mask = torch.empty(batch_size * natom, (natom + 31) // 32, dtype=torch.int32, device=device)
+        _cabi.check(lib.b200md_radius_graph_count_masked(
+            _cabi.ptr(pos), _cabi.ptr(basis), int(positions_are_relative), float(radial_cutoff), batch_size, natom,
+            _cabi.ptr(counts), _cabi.ptr(per_structure), _cabi.ptr(status), _cabi.ptr(hit_mask), stream))
+    else:
+        _cabi.check(lib.b200md_radius_graph_count(
+            _cabi.ptr(pos), _cabi.ptr(basis), int(positions_are_relative), float(radial_cutoff), batch_size, natom, mode,
+            _cabi.ptr(counts), _cabi.ptr(per_structure), _cabi.ptr(status), stream))
     # The reference also synchronises here (int(max_k_array.max()), neighbors.py:181, and the assert :110).
     _cabi.raise_on_status(status, AssertionError)
     inclusive = torch.cumsum(counts, dim=0, dtype=torch.int64)
@@ -54,7 +63,11 @@ def _radius_graph(
     dst = torch.empty(total, dtype=torch.int64, device=device)
     shifts = torch.empty(total, 3, dtype=torch.float32, device=device) if want_shifts else None
     edge_batch = torch.empty(total, dtype=torch.int64, device=device)
-    if total > 0:
+    if total > 0 and one_sweep:
+        _cabi.check(lib.b200md_radius_graph_fill_from_mask(
+            _cabi.ptr(hit_mask), batch_size, natom, _cabi.ptr(offsets), int(node_index_offset), _cabi.ptr(src),
+            _cabi.ptr(dst), _cabi.ptr(edge_batch), stream))
+    elif total > 0:
         _cabi.check(lib.b200md_radius_graph_fill(
             _cabi.ptr(pos), _cabi.ptr(basis), int(positions_are_relative), float(radial_cutoff), batch_size, natom,
             mode, _cabi.ptr(offsets), int(node_index_offset), _cabi.ptr(src), _cabi.ptr(dst), _cabi.ptr(shifts),

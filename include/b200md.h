@@ -241,6 +241,17 @@ int b200md_radius_graph_fill(const float* positions, const float* cell,
                              int64_t node_index_offset, int64_t* src_out, int64_t* dst_out,
                              float* shifts_out_or_null, int64_t* edge_batch_or_null,
                              b200md_stream_t stream);
+/* One sweep instead of two for the unique-pair form without shifts (get_edges_with_radial_cutoff,
+ * models/egnn_utils.py:107-144): the count pass also writes the hit bit row of every source atom,
+ * hit_mask [B*N, ceil(N/32)] uint32 (bit j of row (b, i): j is a neighbour of i), and the fill expands those rows
+ * (one warp per row; same output order) without the positions. */
+int b200md_radius_graph_count_masked(const float* positions, const float* cell,
+                                     int32_t positions_are_relative, float radial_cutoff, int64_t n_samples,
+                                     int32_t n_atoms, int32_t* counts, int64_t* edges_per_structure,
+                                     int32_t* status, uint32_t* hit_mask, b200md_stream_t stream);
+int b200md_radius_graph_fill_from_mask(const uint32_t* hit_mask, int64_t n_samples, int32_t n_atoms,
+                                       const int64_t* offsets, int64_t node_index_offset, int64_t* src_out,
+                                       int64_t* dst_out, int64_t* edge_batch_or_null, b200md_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pair distances: compute_distances_in_batch (utils/structure_utils.py:41-121), the sample statistic of the
