@@ -281,6 +281,55 @@ def test_edges_with_radial_cutoff_golden(cuda_device, rc):
     assert torch.equal(edges.cpu(), g[f"egnn.edges_rc{rc}"])
 
 
+@pytest.mark.parametrize("N,length,B,rc", [(45, 11.0, 5, 4.0), (33, 9.0, 3, 4.4), (64, 16.5, 7, 7.5), (200, 14.0, 2, 6.5)])
+def test_one_sweep_radius_graph_equals_two_sweeps(cuda_device, N, length, B, rc):
+    """C ABI, called directly: ``b200md_radius_graph_count_masked`` + ``_fill_from_mask`` (the count pass keeps the hit bit
+    rows, the fill expands them) against ``b200md_radius_graph_count`` + ``_fill`` (two sweeps) on a triclinic cell with
+    atoms outside the home cell; atom counts that are not multiples of 32."""
+    lib = _cabi.lib()
+    torch.manual_seed(11)
+    rel = (torch.rand(B, N, 3) * 1.6 - 0.3).to(cuda_device)
+    cell = (torch.diag_embed(torch.full((B, 3), length)) + 0.8 * torch.rand(B, 3, 3)).to(cuda_device)
+    stream = _cabi.stream_ptr(cuda_device)
+    rows = B * N
+
+    def run(one_sweep: bool):
+        counts = torch.empty(rows, dtype=torch.int32, device=cuda_device)
+        per_structure = torch.empty(B, dtype=torch.int64, device=cuda_device)
+        status = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+        mask = torch.full((rows, (N + 31) // 32), -1, dtype=torch.int32, device=cuda_device)
+        if one_sweep:
+            _cabi.check(lib.b200md_radius_graph_count_masked(_cabi.ptr(rel), _cabi.ptr(cell), 1, rc, B, N, _cabi.ptr(counts),
+                                                             _cabi.ptr(per_structure), _cabi.ptr(status), _cabi.ptr(mask), stream))
+        else:
+            _cabi.check(lib.b200md_radius_graph_count(_cabi.ptr(rel), _cabi.ptr(cell), 1, rc, B, N, _cabi.GRAPH_UNIQUE_PAIRS,
+                                                      _cabi.ptr(counts), _cabi.ptr(per_structure), _cabi.ptr(status), stream))
+        assert int(status.item()) == 0
+        inclusive = torch.cumsum(counts, dim=0, dtype=torch.int64)
+        offsets = inclusive - counts
+        total = int(inclusive[-1].item())
+        src = torch.full((total,), -7, dtype=torch.int64, device=cuda_device)
+        dst = torch.full((total,), -7, dtype=torch.int64, device=cuda_device)
+        batch = torch.full((total,), -7, dtype=torch.int64, device=cuda_device)
+        if one_sweep:
+            _cabi.check(lib.b200md_radius_graph_fill_from_mask(_cabi.ptr(mask), B, N, _cabi.ptr(offsets), N, _cabi.ptr(src),
+                                                               _cabi.ptr(dst), _cabi.ptr(batch), stream))
+        else:
+            _cabi.check(lib.b200md_radius_graph_fill(_cabi.ptr(rel), _cabi.ptr(cell), 1, rc, B, N, _cabi.GRAPH_UNIQUE_PAIRS,
+                                                     _cabi.ptr(offsets), N, _cabi.ptr(src), _cabi.ptr(dst), None,
+                                                     _cabi.ptr(batch), stream))
+        return counts.cpu(), per_structure.cpu(), src.cpu(), dst.cpu(), batch.cpu()
+
+    two, one = run(False), run(True)
+    assert int(two[1].sum()) > 0
+    for expected, got in zip(two, one):
+        assert torch.equal(expected, got)
+    # the masked count refuses a missing workspace
+    assert lib.b200md_radius_graph_count_masked(_cabi.ptr(rel), _cabi.ptr(cell), 1, rc, B, N, _cabi.ptr(two[0].to(cuda_device)),
+                                                _cabi.ptr(two[1].to(cuda_device)), _cabi.ptr(torch.zeros(1, dtype=torch.int32, device=cuda_device)),
+                                                None, stream) != 0
+
+
 @pytest.mark.parametrize("N,length,B", [(64, 16.5, 64), (216, 16.29, 8), (512, 21.72, 4), (1, 9.0, 3)])
 def test_edges_with_radial_cutoff_full_size_against_oracle(cuda_device, N, length, B):
     """BASELINE supercells (2x2x2 in the clipped box, 3x3x3, 4x4x4), rc = 7.5: bit-exact sorted edge lists."""
