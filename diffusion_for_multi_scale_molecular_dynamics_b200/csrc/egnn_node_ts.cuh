@@ -18,11 +18,26 @@
 // lane quarter, 32 columns per thread and chunk).
 #pragma once
 
+// The node kernel runs the 12-warp layout of ts_common.cuh (control warpgroup shrunk to 56 registers, the two epilogue
+// warpgroups grown to 224 with setmaxnreg): with 168 registers its epilogue spills 164 bytes per thread, and with 227 KB of
+// shared memory in use there is hardly any L1 for local memory -- A/B on one box 11.2 -> 9.5 ms per step.  (The edge
+// kernel does not spill and is 0.3 ms per launch slower in that layout: it keeps the 10 warps.)
+#ifndef B200MD_NODE_TS_WARPGROUPS
+#define B200MD_NODE_TS_WARPGROUPS 1
+#endif
+#ifndef B200MD_TS_WARPGROUPS
+#define B200MD_TS_WARPGROUPS B200MD_NODE_TS_WARPGROUPS
+#endif
 #include "ts_common.cuh"
 
 #ifndef B200MD_NODE_TS_EXACT_DIV
 #define B200MD_NODE_TS_EXACT_DIV 0
 #endif
+// reciprocals of the SiLU (ts_common.cuh: silu4): 0 = one per element, 1 = one per pair (9.51 -> 9.40 ms per step)
+#ifndef B200MD_NODE_TS_SILU
+#define B200MD_NODE_TS_SILU 1
+#endif
+constexpr int kNodeSilu = B200MD_NODE_TS_SILU;
 #ifndef B200MD_NODE_TS_PIPELINED
 #define B200MD_NODE_TS_PIPELINED 1
 #endif
@@ -551,8 +566,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 #pragma unroll
               for (int j = 0; j < kTsCols / 4; ++j) {
                 const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
-                silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)), v[4 * j + 0], v[4 * j + 1], dep);
-                silu2_dep(fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)), v[4 * j + 2], v[4 * j + 3], dep);
+                silu4<kNodeSilu>(fma2(pack2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), unscale2, pack2(b.x, b.y)),
+                                 fma2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2, pack2(b.z, b.w)),
+                                 v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep);
               }
             } else {
 #pragma unroll
@@ -562,9 +578,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               NODE_TRACE(27, g * 16 + c);
               if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);   // U of the next chunk
 #pragma unroll
-              for (int j = 0; j < kTsCols / 2; ++j)
-                silu2_dep(fma2(pack2(side[2 * j], side[2 * j + 1]), pack2(kF16ActScale, kF16ActScale),
-                               mul2(pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), unscale2)), v[2 * j], v[2 * j + 1], dep);
+              for (int j = 0; j < kTsCols / 4; ++j)
+                silu4<kNodeSilu>(fma2(pack2(side[4 * j], side[4 * j + 1]), pack2(kF16ActScale, kF16ActScale),
+                                      mul2(pack2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), unscale2)),
+                                 fma2(pack2(side[4 * j + 2], side[4 * j + 3]), pack2(kF16ActScale, kF16ActScale),
+                                      mul2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), unscale2)),
+                                 v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep);
             }
             sfu_release(tok_peer, dep);
           };
@@ -656,8 +675,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               NODE_TRACE(34, g * 16 + c);
             }
             if (valid) {
+              float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;   // four chains (one chain of 32 adds was 3.7 % of the stall samples)
 #pragma unroll
-              for (int j = 0; j < kTsCols; ++j) checksum += v[j];
+              for (int j = 0; j < kTsCols; j += 4) { c0 += v[j]; c1 += v[j + 1]; c2 += v[j + 2]; c3 += v[j + 3]; }
+              checksum += (c0 + c1) + (c2 + c3);
             }
           }
           NODE_TRACE(31, g * 16 + c);
