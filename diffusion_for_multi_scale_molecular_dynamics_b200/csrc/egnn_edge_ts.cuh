@@ -571,7 +571,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     auto first_activation_staged = [&](const Edge& ed, int c, uint32_t a_col) {
       const int col0 = c * 64 + part * kTsCols;
       float v[kTsCols];
+      TS_TRACE(20, c);
       cp_async_wait_all();
+      TS_TRACE(25, c);
       if (ed.valid) {
         const uint64_t rad2 = pack2(ed.radial, ed.radial);
         uint64_t s01[kTsCols / 4], s23[kTsCols / 4];
@@ -582,7 +584,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
           s01[j] = add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y));
           s23[j] = add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w));
         }
+        TS_TRACE(24, (uint32_t)(s01[0] ^ s23[kTsCols / 4 - 1]) & 1u);
         if (c + 1 < nk0_pq) stage_request(ed, c + 1);
+        TS_TRACE(26, c);
 #pragma unroll
         for (int j = 0; j < kTsCols / 4; ++j) {
           const float4 wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
@@ -593,6 +597,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #pragma unroll
         for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
       }
+      TS_TRACE(21, __float_as_uint(v[0] + v[kTsCols - 1]) & 1u);
       uint32_t w[kTsCols];
       split_hi_lo(v, w);
       publish(a_col + (uint32_t)col0, w);
