@@ -18,13 +18,17 @@
 // Warps (10): 0 = weight producer, 1 = MMA issuer (converged, elected lane), 2-9 = epilogue: two per TMEM lane quarter,
 // each converting 32 of the 64 columns of a chunk (few, fat epilogue threads: 168 registers each, 32 independent SiLU
 // chains per thread for the SFU pipe).  (ts_common.cuh: B200MD_TS_WARPGROUPS for the 12-warp setmaxnreg layout.)
+//
+// The two CTAs of a cluster are ONE tcgen05 CTA pair by default (B200MD_TS_CTA_PAIR below): M = 256 MMAs issued by the
+// leader, half of every weight part in each CTA's shared memory; warp 1 of the peer forwards barrier completions.
 #pragma once
 
 #include "ts_common.cuh"
 
-// CTAs per thread-block cluster.  With 2, the CTAs of a pair walk the same weight stream: each fetches half of every
-// weight stage from L2 and multicasts it into the shared memory of both, which halves the L2 -> SM weight traffic
-// (117 GB per launch at 4096 structures).  Both CTAs run the same number of tiles (the last one may be empty).
+// CTAs per thread-block cluster.  With 2, the CTAs of a pair walk the same weight stream.  Without B200MD_TS_CTA_PAIR each
+// fetches half of every weight stage from L2 and multicasts it into the shared memory of both (the round-1 scheme); with it
+// each keeps its half only.  Either way the L2 -> SM weight traffic is halved (117 -> 58 GB per launch at 4096 structures).
+// Both CTAs run the same number of tiles (the last one may be empty).
 #ifndef B200MD_TS_CLUSTER
 #define B200MD_TS_CLUSTER 2
 #endif
