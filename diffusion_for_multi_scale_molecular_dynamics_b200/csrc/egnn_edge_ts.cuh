@@ -82,8 +82,19 @@ constexpr int kTsEdgeBStageBytes = (kMaxN / kTsEdgeNSplit) * kRowBytes / (kTsPai
 #ifndef B200MD_TS_PQ_STAGE
 #define B200MD_TS_PQ_STAGE 0
 #endif
+// B200MD_TS_PQ_GATHER = 1: two extra GATHER WARPS (no registers of the epilogue, no L1 lines) bring the P[src] / Q[dst] rows of
+// the NEXT tile's first activation L2 -> shared memory with warp-coalesced cp.async (16 lanes x 16 bytes = one 256-byte row
+// piece, two pieces per instruction) into a ring of two chunk stages ([row][64 columns], rows padded to 272 bytes so that
+// the row-per-lane reads of the epilogue are conflict-free), completion on an mbarrier (cp.async.mbarrier.arrive.noinc).
+// Chunks 0 and 1 are requested as soon as the tile's message layer is over (several layers before their use), chunk c + 2
+// when the eight epilogue warps have read chunk c.  Stage 1 of the Q rows aliases the staging tiles of the segmented sum
+// (idle from the message layer of a tile to that of the next one; the "message layer done" barrier hands them over).
+// Paid for by the weight ring (4 stages of 16 KB; its depth was measured not to matter).
+#ifndef B200MD_TS_PQ_GATHER
+#define B200MD_TS_PQ_GATHER 0
+#endif
 #if !defined(B200MD_TS_EDGE_STAGES) && B200MD_TS_CTA_PAIR
-#define B200MD_TS_EDGE_STAGES (B200MD_TS_PQ_STAGE ? 8 : 10)
+#define B200MD_TS_EDGE_STAGES (B200MD_TS_PQ_GATHER ? 4 : (B200MD_TS_PQ_STAGE ? 8 : 10))
 #endif
 #ifndef B200MD_TS_NEXT_EDGE_AHEAD
 #define B200MD_TS_NEXT_EDGE_AHEAD 0
@@ -95,16 +106,29 @@ constexpr int kTsEdgeBStages = B200MD_TS_EDGE_STAGES;
 constexpr int kTsSegTileBytes = 32 * kTsCols * 4;
 static_assert(!B200MD_TS_SEG_SMEM || kTsCols == 32, "segment_add maps one lane to one column");
 static_assert(!B200MD_TS_PQ_STAGE || (B200MD_TS_SEG_SMEM && kTsCols == 32), "the Q slots alias the segmented-sum tiles (32 x 128 B per warp)");
+constexpr bool kTsGather = B200MD_TS_PQ_GATHER != 0;
+static_assert(!kTsGather || (B200MD_TS_SEG_SMEM && !B200MD_TS_PQ_STAGE && B200MD_TS_CTA_PAIR), "gather warps: CTA-pair ring, Q stage 1 aliases the segmented-sum tiles");
+// the gather warps: the two idle warps of the control warpgroup (B200MD_TS_WARPGROUPS) or two warps behind the epilogue warps
+// (a 10-warp block is handed the registers of 12 anyway)
+constexpr int kTsGatherWarp0 = B200MD_TS_WARPGROUPS ? 2 : kTsFirstEpiWarp + kTsEpiWarps;
+constexpr int kTsEdgeThreads = kTsThreads + ((kTsGather && !B200MD_TS_WARPGROUPS) ? 64 : 0);
+constexpr int kTsPqRowBytes = 64 * 4 + 16;                 // one chunk of a row + 16 bytes: row stride = 17 x 16 bytes
+constexpr int kTsPqStageBytes = kTileM * kTsPqRowBytes;    // 34 KB
 struct TsSmem {
-  uint32_t b, seg, pslot, bars, tmem_slot, bias, scale, wr, wlast, dot, total;
+  uint32_t b, seg, qx, q0, pst, pslot, bars, tmem_slot, bias, scale, wr, wlast, dot, total;
 };
 __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   TsSmem L;
   uint32_t o = 0;
   L.b = o; o += kTsEdgeBStages * kTsEdgeBStageBytes;
   L.seg = o; o += B200MD_TS_SEG_SMEM ? kTsEpiWarps * kTsSegTileBytes : 0;
+  // gather stages: Q stage 1 = [seg tiles | qx] (contiguous), Q stage 0, P stages 0 and 1
+  L.qx = o; o += kTsGather ? kTsPqStageBytes - kTsEpiWarps * kTsSegTileBytes : 0;
+  L.q0 = o; o += kTsGather ? kTsPqStageBytes : 0;
+  L.pst = o; o += kTsGather ? 2 * kTsPqStageBytes : 0;
   L.pslot = o; o += B200MD_TS_PQ_STAGE ? kTsEpiWarps * kTsSegTileBytes : 0;
-  L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsEdgeNSplit) * 8;
+  L.bars = o; o += (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsEdgeNSplit + 5) * 8;
+  o = (o + 15u) & ~15u;   // what follows is read with 128-bit loads
   L.tmem_slot = o; o += 16;
   L.bias = o; o += (uint32_t)n_gemms * kMaxN * 4;
   L.scale = o; o += 16 * 4;   // 2^-s of each GEMM's fp16 weight image (tc_common.cuh)
@@ -145,6 +169,13 @@ struct TsPipe {
   __device__ __forceinline__ uint32_t acc_full(uint32_t buf, uint32_t group) const {
     return bar0 + 8u * (2 * kTsEdgeBStages + kTsSlots * kTsParts + buf * kTsEdgeNSplit + group);
   }
+  // gather ring (B200MD_TS_PQ_GATHER): "stage s holds a chunk" (the 64 gather lanes' copies have landed), "stage s has
+  // been read" (8 epilogue warps), "the message layer of this tile is over" (8 epilogue warps: the seg tiles are free)
+  __device__ __forceinline__ uint32_t pq_full(uint32_t s) const {
+    return bar0 + 8u * (2 * kTsEdgeBStages + kTsSlots * kTsParts + 2 * kTsEdgeNSplit + s);
+  }
+  __device__ __forceinline__ uint32_t pq_empty(uint32_t s) const { return pq_full(s) + 16u; }
+  __device__ __forceinline__ uint32_t msg_done() const { return pq_full(0) + 32u; }
 };
 
 // B200MD_TS_PQ_AHEAD = 1 requests the P / Q rows of the next tile one chunk ahead of their use (needs the registers of
@@ -152,7 +183,7 @@ struct TsPipe {
 #ifndef B200MD_TS_PQ_AHEAD
 #define B200MD_TS_PQ_AHEAD 0
 #endif
-__global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeTcArgs a) {
+__global__ void __launch_bounds__(kTsEdgeThreads, 1) egnn_edge_ts_kernel(const EdgeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const Program& p = a.prog;
@@ -167,11 +198,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
   const int n_tiles = (E + kTileM - 1) / kTileM;
   const int M = a.M;
 
-  for (int t = threadIdx.x; t < p.n_gemms * kMaxN; t += kTsThreads) {
+  for (int t = threadIdx.x; t < p.n_gemms * kMaxN; t += kTsEdgeThreads) {
     const int g = t / kMaxN, n = t - g * kMaxN;
     s_bias[t] = (n < p.gN[g] && p.gB[g] >= 0) ? p.packed[p.gB[g] + n] * kF16ActScale : 0.f;   // x kF16ActScale: ts_common.cuh
   }
-  for (int t = threadIdx.x; t < kMaxN; t += kTsThreads) {
+  for (int t = threadIdx.x; t < kMaxN; t += kTsEdgeThreads) {
     s_wr[t] = (t < M) ? p.packed[a.msg_wr + t] : 0.f;
     s_wlast[t] = (t < p.gN[p.n_gemms - 1]) ? p.packed[a.coord_last_w + t] : 0.f;
   }
@@ -189,6 +220,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     for (int s = 0; s < kTsSlots; ++s)
       for (int j = 0; j < kTsParts; ++j) mbar_init(pipe.a_full(s, j), pair_leader ? 5 : 4);
     for (int s = 0; s < 2 * kTsEdgeNSplit; ++s) mbar_init(pipe.acc_full(s / kTsEdgeNSplit, s % kTsEdgeNSplit), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(pipe.pq_full(s), 64); mbar_init(pipe.pq_empty(s), kTsEpiWarps); }
+    mbar_init(pipe.msg_done(), kTsEpiWarps);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -216,11 +249,43 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 
   // setmaxnreg sits at the top of each warpgroup's branch: ptxas budgets the code a setmaxnreg dominates (after a merge
   // of the two branches it would compile everything for the smaller value)
-  if (warp < kTsFirstEpiWarp) {
+  if (warp < kTsFirstEpiWarp || warp >= kTsFirstEpiWarp + kTsEpiWarps) {
 #if B200MD_TS_WARPGROUPS
   ts_regs_release<kTsRegsControl>();
 #endif
-  if (warp == 0) {
+  if (kTsGather && warp >= kTsGatherWarp0 && warp < kTsGatherWarp0 + 2) {
+    // ===== gather warps: rows [64 gw, 64 gw + 64) of the NEXT tile's P[src] / Q[dst] chunks -> shared memory =====
+    const int gw = warp - kTsGatherWarp0, nk0 = a.M / 64;
+    const uint32_t p_st = pipe.s_base + L.pst, q_st0 = pipe.s_base + L.q0, q_st1 = pipe.s_base + L.seg;
+    const uint32_t piece = (uint32_t)(lane & 15);
+    uint32_t n = 0;   // running chunk index: stage n & 1
+    if (a.n_msg > 0)
+      for (int it = 0; it + 1 < n_iterations; ++it) {
+        const int e0 = (first_tile + (it + 1) * tile_stride) * kTileM + 64 * gw + lane;
+        const int s_lo = e0 < E ? a.edge_src[e0] : -1, s_hi = e0 + 32 < E ? a.edge_src[e0 + 32] : -1;
+        const int d_lo = e0 < E ? a.edge_dst[e0] : 0, d_hi = e0 + 32 < E ? a.edge_dst[e0 + 32] : 0;
+        mbar_wait(pipe.msg_done(), (uint32_t)it & 1u);   // the seg tiles (Q stage 1) are free
+        for (int c = 0; c < nk0; ++c, ++n) {
+          const uint32_t s = n & 1u;
+          mbar_wait(pipe.pq_empty(s), ((n >> 1) & 1u) ^ 1u);
+          const uint32_t p_row0 = p_st + s * kTsPqStageBytes + (uint32_t)(64 * gw) * kTsPqRowBytes + piece * 16u;
+          const uint32_t q_row0 = (s ? q_st1 : q_st0) + (uint32_t)(64 * gw) * kTsPqRowBytes + piece * 16u;
+          const float* pc = a.P + c * 64 + piece * 4;
+          const float* qc = a.Q + c * 64 + piece * 4;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {   // two rows per instruction: lanes 0-15 row 2 i, lanes 16-31 row 2 i + 1
+            const int r = 2 * i + (lane >> 4);
+            const int src = __shfl_sync(0xffffffffu, i < 16 ? s_lo : s_hi, r & 31);
+            const int dst = __shfl_sync(0xffffffffu, i < 16 ? d_lo : d_hi, r & 31);
+            if (src >= 0) {
+              cp_async16(p_row0 + (uint32_t)r * kTsPqRowBytes, pc + (int64_t)src * a.M);
+              cp_async16(q_row0 + (uint32_t)r * kTsPqRowBytes, qc + (int64_t)dst * a.M);
+            }
+          }
+          cp_async_mbar_arrive_noinc(pipe.pq_full(s));
+        }
+      }
+  } else if (warp == 0) {
     // ===== weight producer =====
     if (lane == 0) {
       uint32_t cb = 0;
@@ -608,6 +673,43 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
     };
 #endif
 
+#if B200MD_TS_PQ_GATHER
+    // chunk c of the NEXT tile's first activation from the gather ring (its rows were requested by the gather warps long
+    // before): wait for the stage, read this row's two 128-byte pieces, hand the stage back
+    const bool gathered = a.n_msg > 0;   // without a hidden message layer segment_add runs inside the first activation
+    uint32_t pqn = 0;
+    const uint32_t pq_row = (uint32_t)row * kTsPqRowBytes + (uint32_t)part * (kTsCols * 4);
+    auto first_activation_gathered = [&](const Edge& ed, int c, uint32_t a_col) {
+      const int col0 = c * 64 + part * kTsCols;
+      const uint32_t s = pqn & 1u;
+      float v[kTsCols];
+      TS_TRACE(20, c);
+      mbar_wait(pipe.pq_full(s), (pqn >> 1) & 1u);
+      TS_TRACE(25, c);
+      if (ed.valid) {
+        const uint64_t rad2 = pack2(ed.radial, ed.radial);
+        const uint32_t p_at = pipe.s_base + L.pst + s * kTsPqStageBytes + pq_row;
+        const uint32_t q_at = pipe.s_base + (s ? L.seg : L.q0) + pq_row;
+#pragma unroll
+        for (int j = 0; j < kTsCols / 4; ++j) {
+          const float4 pv = lds128_ordered(p_at + 16u * j), qv = lds128_ordered(q_at + 16u * j), wv = lds128(sa_wr + (uint32_t)(col0 + 4 * j) * 4u);
+          silu4<kTsEdgeSilu>(mul2(fma2(rad2, pack2(wv.x, wv.y), add2(pack2(pv.x, pv.y), pack2(qv.x, qv.y))), act2), mul2(fma2(rad2, pack2(wv.z, wv.w), add2(pack2(pv.z, pv.w), pack2(qv.z, qv.w))), act2),
+                             v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep_first);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTsCols; ++j) v[j] = 0.f;
+      }
+      TS_TRACE(21, __float_as_uint(v[0] + v[kTsCols - 1]) & 1u);
+      uint32_t w[kTsCols];
+      split_hi_lo(v, w);   // every v depends on the stage's reads: they have completed by the time the stage is handed back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pipe.pq_empty(s));
+      ++pqn;
+      publish(a_col + (uint32_t)col0, w);
+    };
+#endif
+
     const int nk0 = M / 64;
     const int n_last = p.gN[p.n_gemms - 1] / 64;   // chunks of the last accumulator
     Edge cur{};
@@ -717,6 +819,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               TS_TRACE(16, g * 16 + c);
               segment_add(cur, v, a.agg, M, col0);  // agg[src] += m (models/egnn.py:178-181)
               TS_TRACE(17, g * 16 + c);
+#if B200MD_TS_PQ_GATHER
+              if (!more && lane == 0) mbar_arrive(pipe.msg_done());   // (segment_add ends with a __syncwarp) the seg tiles are free
+#endif
             }
             if (more) {
               TS_TRACE(12, g * 16 + c);
@@ -760,6 +865,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
 #elif B200MD_TS_PQ_STAGE
               if (stage_pq) first_activation_staged(next, c, d_col);
               else first_activation_chunk(next, c, d_col);
+#elif B200MD_TS_PQ_GATHER
+              if (gathered) first_activation_gathered(next, c, d_col);
+              else first_activation_chunk(next, c, d_col);
 #else
               if (c + 1 < nk0) prefetch_first(next, c + 1);
               first_activation_chunk(next, c, d_col);
@@ -773,6 +881,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_edge_ts_kernel(const EdgeT
               if (c + 1 < nk0) load_pq(next, c + 1, ahead);
 #elif B200MD_TS_PQ_STAGE
               if (stage_pq) first_activation_staged(next, c, d_col);
+              else first_activation_chunk(next, c, d_col);
+#elif B200MD_TS_PQ_GATHER
+              if (gathered) first_activation_gathered(next, c, d_col);
               else first_activation_chunk(next, c, d_col);
 #else
               if (c + 1 < nk0) prefetch_first(next, c + 1);

@@ -382,7 +382,7 @@ int tc_launch_edge_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, i
     if (kTsCluster > 1) {
       cudaLaunchConfig_t cfg_l{};
       cfg_l.gridDim = dim3((unsigned)(tc_sm_count() / kTsCluster) * kTsCluster);
-      cfg_l.blockDim = dim3(kTsThreads);
+      cfg_l.blockDim = dim3(kTsEdgeThreads);
       cfg_l.dynamicSmemBytes = smem;
       cfg_l.stream = st;
       cudaLaunchAttribute attr[1];
@@ -393,7 +393,7 @@ int tc_launch_edge_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, i
       cudaError_t e = cudaLaunchKernelEx(&cfg_l, egnn_edge_ts_kernel, a);
       if (e != cudaSuccess) return set_cuda_error(e);
     } else {
-      egnn_edge_ts_kernel<<<(unsigned)tc_sm_count(), kTsThreads, smem, st>>>(a);
+      egnn_edge_ts_kernel<<<(unsigned)tc_sm_count(), kTsEdgeThreads, smem, st>>>(a);
     }
   } else {
     ProfileScope ps__(B200MD_KERNEL_EDGE, st);

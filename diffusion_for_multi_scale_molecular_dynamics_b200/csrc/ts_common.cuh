@@ -318,6 +318,10 @@ __device__ __forceinline__ float4 lds128_ordered(uint32_t saddr) {
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
+// this thread's arrival on `bar` happens when all its cp.async issued so far have landed (the barrier's count includes it)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
