@@ -101,7 +101,35 @@ __device__ unsigned g_node_trace_count;
 
 // Weight ring of the node kernel: 10 stages of 16 KB (the 12 of ts_common.cuh minus the 32 KB of row staging below; the
 // producer is always ahead of the MMAs -- it waits on "stage empty" for most of its life -- so two stages less cost nothing).
-constexpr int kNodeBStages = 10;
+// B200MD_NODE_TS_INPUT_WARPS = 1: the two idle warps of the control warpgroup bring every row the epilogue READS from global
+// memory -- the agg rows of the tile's first A operand, the U rows of the first layer, the residual h rows of the last one, in
+// that order, one 64-column chunk of the tile's 128 rows at a time -- into a ring of shared-memory stages with warp-coalesced
+// cp.async (16 lanes x 16 bytes = one row piece; XOR-swizzled 16-byte groups, conflict-free for the row-per-lane reads),
+// completion on an mbarrier.  The chunks run ahead of their use by the depth of the ring, across layer and TILE boundaries
+// (the next tile's first agg chunks arrive while the outputs of this one are drained), with no register of the epilogue
+// threads and no exposed L2 / HBM round trip on the tile's serial chain.  Paid for by the weight ring.
+#ifndef B200MD_NODE_TS_INPUT_WARPS
+#define B200MD_NODE_TS_INPUT_WARPS 1
+#endif
+#ifndef B200MD_NODE_TS_IN_STAGES
+#define B200MD_NODE_TS_IN_STAGES 2
+#endif
+// B200MD_NODE_TS_DRAIN_PIPELINED = 1 (needs the registers the input warps free): in the layers WITHOUT a SiLU (the last chain
+// layer and the P / Q / U outputs) the accumulator columns of chunk c + 1 are requested (tcgen05.ld) before chunk c is stored to
+// global memory, a column group is reported drained as soon as it is in registers (not after its rows have been stored), and
+// h' is published as the next A operand before it is stored.
+#ifndef B200MD_NODE_TS_DRAIN_PIPELINED
+#define B200MD_NODE_TS_DRAIN_PIPELINED 1
+#endif
+static_assert(!B200MD_NODE_TS_DRAIN_PIPELINED || (B200MD_NODE_TS_INPUT_WARPS && B200MD_NODE_TS_PIPELINED), "the pipelined drain reads its side rows from the input ring and handles the layers without a SiLU only");
+constexpr bool kNodeInputWarps = B200MD_NODE_TS_INPUT_WARPS != 0;
+static_assert(!kNodeInputWarps || B200MD_TS_WARPGROUPS, "the input warps are warps 2 and 3 of the control warpgroup");
+constexpr int kNodeInStages = kNodeInputWarps ? B200MD_NODE_TS_IN_STAGES : 0;
+constexpr int kNodeInStageBytes = kTileM * 64 * 4;   // 128 rows x one 64-column chunk
+#ifndef B200MD_NODE_TS_B_STAGES
+#define B200MD_NODE_TS_B_STAGES (B200MD_NODE_TS_INPUT_WARPS ? 10 - 2 * B200MD_NODE_TS_IN_STAGES : 10)
+#endif
+constexpr int kNodeBStages = B200MD_NODE_TS_B_STAGES;
 static_assert(kNodeBStages % 2 == 0, "the MMA loop consumes the hi / lo stages of a K chunk in pairs");
 // Row staging: 32 rows x 128 B per epilogue warp.  A TMEM lane is a ROW, so an epilogue thread owns 128 contiguous bytes
 // of one row and a warp-wide 128-bit access touches 32 different lines: 32 L1 wavefronts per instruction, 2048 per 64-column
@@ -113,14 +141,15 @@ static_assert(kNodeBStages % 2 == 0, "the MMA loop consumes the hi / lo stages o
 #endif
 constexpr int kNodeStageBytes = 32 * 128;
 struct NodeTsSmem {
-  uint32_t b, stage, bars, tmem_slot, bias, scale, readout, logits, total;
+  uint32_t b, stage, in, bars, tmem_slot, bias, scale, readout, logits, total;
 };
 __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   NodeTsSmem L;
   uint32_t o = 0;
   L.b = o; o += kNodeBStages * kTsBStageBytes;
   L.stage = o; o += kTsEpiWarps * kNodeStageBytes;
-  L.bars = o; o += (2 * kNodeBStages + kTsSlots * kTsParts + 2 * kTsNSplit + kTsNSplit) * 8;
+  L.in = o; o += kNodeInStages * kNodeInStageBytes;
+  L.bars = o; o += (2 * kNodeBStages + kTsSlots * kTsParts + 2 * kTsNSplit + kTsNSplit + 2 * kNodeInStages) * 8;
   L.tmem_slot = o; o += 16;
   o = (o + 15u) & ~15u;   // the bias rows are read with 128-bit shared loads
   L.bias = o; o += (uint32_t)(n_gemms > 0 ? n_gemms : 1) * kMaxN * 4;
@@ -145,6 +174,11 @@ struct NodeTsBars {
   __device__ __forceinline__ uint32_t d_free(uint32_t group) const {
     return bar0 + 8u * (2 * kNodeBStages + kTsSlots * kTsParts + 2 * kTsNSplit + group);
   }
+  // input ring (B200MD_NODE_TS_INPUT_WARPS): "stage s holds a chunk" (64 input lanes), "stage s has been read" (8 epilogue warps)
+  __device__ __forceinline__ uint32_t in_full(uint32_t s) const {
+    return bar0 + 8u * (2 * kNodeBStages + kTsSlots * kTsParts + 3 * kTsNSplit + s);
+  }
+  __device__ __forceinline__ uint32_t in_empty(uint32_t s) const { return in_full(s) + 8u * kNodeInStages; }
 };
 
 __device__ __forceinline__ float4 lds128_staged(uint32_t saddr) {   // ordered against the staging stores (volatile, clobber)
@@ -194,6 +228,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       for (int j = 0; j < kTsParts; ++j) mbar_init(bars.a_full(s, j), 4);
     for (int s = 0; s < 2 * kTsNSplit; ++s) mbar_init(bars.acc_full(s / kTsNSplit, s % kTsNSplit), 1);
     for (int s = 0; s < kTsNSplit; ++s) mbar_init(bars.d_free(s), kTsEpiWarps);
+    for (int s = 0; s < kNodeInStages; ++s) { mbar_init(bars.in_full(s), 64); mbar_init(bars.in_empty(s), kTsEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_base + L.tmem_slot, kTmemCols);
@@ -233,6 +268,39 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                        bytes, bars.b_full(s));
             }
         }
+    }
+  } else if (kNodeInputWarps && warp >= 2) {
+    // ===== input warps: rows [64 hw, 64 hw + 64) of every chunk the epilogue reads, in the epilogue's order =====
+    const int hw = warp - 2;
+    const uint32_t piece = (uint32_t)(lane & 15);
+    const uint32_t in_base = s_base + L.in;
+    uint32_t n = 0;
+    auto fill = [&](const float* rows, int ld, int col, int64_t row0, int rows_valid_tile) {
+      const uint32_t s = n % (uint32_t)(kNodeInStages > 0 ? kNodeInStages : 1);
+      mbar_wait(bars.in_empty(s), ((n / (uint32_t)(kNodeInStages > 0 ? kNodeInStages : 1)) & 1u) ^ 1u);
+      const uint32_t dst0 = in_base + s * kNodeInStageBytes;
+      const float* src0 = rows + row0 * ld + col + piece * 4;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {   // two rows per instruction: lanes 0-15 row 2 i, lanes 16-31 row 2 i + 1
+        const int r = 64 * hw + 2 * i + (lane >> 4);
+        if (r < rows_valid_tile) cp_async16(dst0 + (uint32_t)r * 256u + ((piece ^ (uint32_t)(r & 7)) << 4), src0 + (int64_t)r * ld);
+      }
+      cp_async_mbar_arrive_noinc(bars.in_full(s));
+      ++n;
+    };
+    for (int it = 0; it < n_iterations; ++it) {
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileM;
+      const int rows_valid_tile = (int)max((int64_t)0, min((int64_t)kTileM, a.n_nodes - row0));
+      if (!a.do_embed)
+        for (int c = 0; c < M / 64; ++c) fill(a.agg, M, c * 64, row0, rows_valid_tile);
+      for (int g = 0; g < a.n_gemms; ++g) {
+        const NodeTsGemm& G = a.g[g];
+        const float* side_rows = nullptr;
+        if (G.kind == kNodeChainAddU) side_rows = a.U;
+        if (G.kind == kNodeChainLast && a.residual) side_rows = a.h;
+        if (side_rows != nullptr)
+          for (int c = 0; c < G.N / 64; ++c) fill(side_rows, H, c * 64, row0, rows_valid_tile);
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp converged, elected lane issues; see egnn_edge_ts.cuh) =====
@@ -307,6 +375,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     const uint32_t sa_bias = s_base + L.bias;
     const uint32_t stage = s_base + L.stage + (uint32_t)(warp - kTsFirstEpiWarp) * kNodeStageBytes;
     uint32_t ca = 0, abuf = 0;
+    uint32_t inq = 0;   // chunks taken from the input ring
+    (void)inq;
     uint32_t uses[2] = {0u, 0u};
     unsigned local_status = 0;
     float checksum = 0.f;   // inf / NaN of an fp16 overflow propagates into everything stored: one test at the end
@@ -420,6 +490,23 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         }
 #endif
       };
+#if B200MD_NODE_TS_INPUT_WARPS
+      // this lane's row of the next chunk of the input ring (rows beyond the end read as zero)
+      auto input_collect = [&](float (&v)[kTsCols]) {
+        const uint32_t s = inq % (uint32_t)kNodeInStages;
+        mbar_wait(bars.in_full(s), (inq / (uint32_t)kNodeInStages) & 1u);
+        const uint32_t at = s_base + L.in + s * kNodeInStageBytes + (uint32_t)row * 256u + (uint32_t)part * 128u;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) f = lds128_staged(at + (uint32_t)((p ^ (lane & 7)) << 4));
+          v[4 * p] = f.x; v[4 * p + 1] = f.y; v[4 * p + 2] = f.z; v[4 * p + 3] = f.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.in_empty(s));
+        ++inq;
+      };
+#endif
       float sg = 0.f;
       int atc = 0;
       if (a.do_embed && valid) {
@@ -493,16 +580,23 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       } else {
         // aggregated messages (mean: / max(deg, 1)), reset for the next layer   models/egnn.py:178-183
         // (the rows of chunk c + 1 are requested before chunk c is converted and published)
+#if !B200MD_NODE_TS_INPUT_WARPS
         RowTile ahead;
         rows_request(a.agg, M, part * kTsCols, ahead);
+#endif
         for (int c = 0; c < M / 64; ++c) {
           const int col0 = c * 64 + part * kTsCols;
           float v[kTsCols];
           NODE_TRACE(22, c);
+#if B200MD_NODE_TS_INPUT_WARPS
+          input_collect(v);
+          NODE_TRACE(23, c);
+#else
           rows_collect(ahead, v);   // the loads have returned here: the reset below may follow (a store issued right
                                     // behind loads of the same addresses doubles the time of the whole kernel, measured)
           NODE_TRACE(23, c);
           if (c + 1 < M / 64) rows_request(a.agg, M, col0 + 64, ahead);
+#endif
           if (a.message_mean) {
 #pragma unroll
             for (int j = 0; j < kTsCols; ++j) v[j] = B200MD_NODE_TS_EXACT_DIV ? v[j] / degf : v[j] * inv_deg;
@@ -539,8 +633,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         const float* side_rows = nullptr;   // warp-uniform
         if (G.kind == kNodeChainAddU) side_rows = a.U;
         if (G.kind == kNodeChainLast && a.residual) side_rows = a.h;
+#if !B200MD_NODE_TS_INPUT_WARPS
         RowTile side_tile;
         rows_request(side_rows, H, part * kTsCols, side_tile);
+#endif
         auto wait_for_chunk = [&](int c) {
           const int need = ts_last_group_of_chunk(c, nh);
           if (need > waited) {
@@ -574,9 +670,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 #pragma unroll
               float side[kTsCols];
               NODE_TRACE(26, g * 16 + c);
+#if B200MD_NODE_TS_INPUT_WARPS
+              input_collect(side);
+              NODE_TRACE(27, g * 16 + c);
+#else
               rows_collect(side_tile, side);
               NODE_TRACE(27, g * 16 + c);
               if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);   // U of the next chunk
+#endif
 #pragma unroll
               for (int j = 0; j < kTsCols / 4; ++j)
                 silu4<kNodeSilu>(fma2(pack2(side[4 * j], side[4 * j + 1]), pack2(kF16ActScale, kF16ActScale),
@@ -612,6 +713,82 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           continue;
         }
 #endif
+#if B200MD_NODE_TS_DRAIN_PIPELINED
+        {
+          uint32_t r[kTsCols];
+          wait_for_chunk(0);
+#pragma unroll
+          for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(lane_taddr + d_col + part * kTsCols + 16 * i, r + 16 * i);
+          for (int c = 0; c < nchunks; ++c) {
+            const int col0 = c * 64 + part * kTsCols;
+            const bool more = c + 1 < nchunks;
+            float v[kTsCols];
+#pragma unroll
+            for (int i = 0; i < kTsCols / 16; ++i) tmem_ld_wait16(r + 16 * i);
+            NODE_TRACE(28, g * 16 + c);
+            if (G.signal_d_free) {   // every column group that ends inside this chunk is in registers: the next output's MMAs may overwrite it
+#pragma unroll
+              for (int h = 0; h < kTsNSplit; ++h)
+                if ((h + 1) * nh > c * 64 && (h + 1) * nh <= (c + 1) * 64) {
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bars.d_free(h));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kTsCols / 4; ++j) {
+              const float4 b = lds128(bias + (uint32_t)(col0 + 4 * j) * 4u);
+              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), unscale_true, b.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), unscale_true, b.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), unscale_true, b.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), unscale_true, b.w);
+            }
+            if (more) {   // the next chunk's accumulator columns travel under this chunk's stores
+              wait_for_chunk(c + 1);
+#pragma unroll
+              for (int i = 0; i < kTsCols / 16; ++i) tmem_ld16_issue(lane_taddr + d_col + col0 + 64 + 16 * i, r + 16 * i);
+            }
+            if (side_rows != nullptr) {   // warp-uniform: the residual h
+              float u[kTsCols];
+              input_collect(u);
+              NODE_TRACE(29, g * 16 + c);
+#pragma unroll
+              for (int j = 0; j < kTsCols; ++j) v[j] = u[j] + v[j];
+            }
+            if (becomes_a) publish(d_col + (uint32_t)col0, v, kF16ActScale);   // h' is the A operand of the outputs
+            NODE_TRACE(30, g * 16 + c);
+            if (G.kind == kNodeChainLast) {
+              rows_store(a.h, H, col0, v);
+              if (a.do_readout) {   // logits = W_c h + b_c (egnn.py:379): partial dot products while h' is in registers
+#pragma unroll
+                for (int cl = 0; cl < kNodeMaxClasses; ++cl)
+                  if (cl < a.C) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kTsCols / 4; ++j) {
+                      const float4 w = *reinterpret_cast<const float4*>(s_readout + cl * kMaxN + col0 + 4 * j);
+                      acc = fmaf(v[4 * j + 0], w.x, acc); acc = fmaf(v[4 * j + 1], w.y, acc);
+                      acc = fmaf(v[4 * j + 2], w.z, acc); acc = fmaf(v[4 * j + 3], w.w, acc);
+                    }
+                    logit[cl] += acc;
+                  }
+              }
+            } else {
+              rows_store(G.out, G.N, col0, v);
+            }
+            NODE_TRACE(34, g * 16 + c);
+            if (valid) {
+              float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+              for (int j = 0; j < kTsCols; j += 4) { c0 += v[j]; c1 += v[j + 1]; c2 += v[j + 2]; c3 += v[j + 3]; }
+              checksum += (c0 + c1) + (c2 + c3);
+            }
+          }
+          ++uses[dbuf];
+          if (becomes_a) abuf ^= 1u;
+          continue;
+        }
+#endif
         for (int c = 0; c < nchunks; ++c) {
           wait_for_chunk(c);
           const int col0 = c * 64 + part * kTsCols;
@@ -621,10 +798,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
           NODE_TRACE(28, g * 16 + c);
           float u[kTsCols];
           if (side_rows != nullptr) {   // warp-uniform
+#if B200MD_NODE_TS_INPUT_WARPS
+            input_collect(u);
+            NODE_TRACE(29, g * 16 + c);
+#else
             rows_collect(side_tile, u);
             NODE_TRACE(29, g * 16 + c);
             if (c + 1 < nchunks) rows_request(side_rows, H, col0 + 64, side_tile);
             NODE_TRACE(32, g * 16 + c);
+#endif
           }
           if (G.kind == kNodeChain) {
 #pragma unroll
