@@ -122,6 +122,18 @@ __device__ unsigned g_node_trace_count;
 #define B200MD_NODE_TS_DRAIN_PIPELINED 1
 #endif
 static_assert(!B200MD_NODE_TS_DRAIN_PIPELINED || (B200MD_NODE_TS_INPUT_WARPS && B200MD_NODE_TS_PIPELINED), "the pipelined drain reads its side rows from the input ring and handles the layers without a SiLU only");
+// B200MD_NODE_TS_EARLY_X = 1: the loads of the coordinate update (x += agg_x: first 8 coordinates of the row) and the NEXT
+// tile's degree are issued at the top of the tile, so that their round trips run under the first A operand instead of on
+// the critical path of the part-0 warps (cycle trace r02e: 4.5 k cycles between the first A operand and their first epilogue).
+#ifndef B200MD_NODE_TS_EARLY_X
+#define B200MD_NODE_TS_EARLY_X 1
+#endif
+// B200MD_NODE_TS_L2_AHEAD = 1: when the input warps have requested the last chunk of a tile, they prefetch into the L2 the
+// chunks of the NEXT tile that the ring cannot hold yet (agg chunks 2, 3, ...): requested later, behind this tile's
+// output stores, they took 4 - 6 k cycles to arrive (trace r02e).  2: also the next tile's U rows.
+#ifndef B200MD_NODE_TS_L2_AHEAD
+#define B200MD_NODE_TS_L2_AHEAD 0
+#endif
 constexpr bool kNodeInputWarps = B200MD_NODE_TS_INPUT_WARPS != 0;
 static_assert(!kNodeInputWarps || B200MD_TS_WARPGROUPS, "the input warps are warps 2 and 3 of the control warpgroup");
 constexpr int kNodeInStages = kNodeInputWarps ? B200MD_NODE_TS_IN_STAGES : 0;
@@ -301,6 +313,24 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
         if (side_rows != nullptr)
           for (int c = 0; c < G.N / 64; ++c) fill(side_rows, H, c * 64, row0, rows_valid_tile);
       }
+#if B200MD_NODE_TS_L2_AHEAD
+      if (it + 1 < n_iterations) {
+        const int64_t next0 = row0 + (int64_t)gridDim.x * kTileM;
+        const int next_valid = (int)max((int64_t)0, min((int64_t)kTileM, a.n_nodes - next0));
+        // one 128-byte line per lane and instruction: lanes 0-15 / 16-31 cover rows 2 i, 2 i + 1, lane & 15 the line of the row
+        auto l2_ahead = [&](const float* rows, int ld, int first_col, int n_cols) {
+          if ((lane & 15) * 32 >= n_cols) return;   // 128-byte lines per row: n_cols / 32
+          const int r0 = 64 * hw + (lane >> 4);
+          const float* line = rows + (next0 + r0) * ld + first_col + (lane & 15) * 32;
+#pragma unroll 1
+          for (int r = r0; r < 64 * hw + 64 && r < next_valid; r += 2, line += 2 * (int64_t)ld) prefetch_l2(line);
+        };
+        if (!a.do_embed && M > kNodeInStages * 64) l2_ahead(a.agg, M, kNodeInStages * 64, M - kNodeInStages * 64);
+#if B200MD_NODE_TS_L2_AHEAD > 1
+        if (a.do_update) l2_ahead(a.U, H, 0, H);
+#endif
+      }
+#endif
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp converged, elected lane issues; see egnn_edge_ts.cuh) =====
@@ -375,6 +405,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     const uint32_t sa_bias = s_base + L.bias;
     const uint32_t stage = s_base + L.stage + (uint32_t)(warp - kTsFirstEpiWarp) * kNodeStageBytes;
     uint32_t ca = 0, abuf = 0;
+    int32_t deg_next = 1;   // B200MD_NODE_TS_EARLY_X: the next tile's degree of this row
+    (void)deg_next;
     uint32_t inq = 0;   // chunks taken from the input ring
     (void)inq;
     uint32_t uses[2] = {0u, 0u};
@@ -410,7 +442,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int64_t node = (int64_t)tile * kTileM + row;
       const bool valid = node < a.n_nodes;
+#if B200MD_NODE_TS_EARLY_X
+      if (it == 0) deg_next = valid ? a.deg[node] : 1;
+      const float degf = fmaxf((float)deg_next, 1.0f);
+      {
+        const int64_t node_next = node + (int64_t)gridDim.x * kTileM;
+        deg_next = (it + 1 < n_iterations && node_next < a.n_nodes) ? a.deg[node_next] : 1;
+      }
+#else
       const float degf = valid ? fmaxf((float)a.deg[node], 1.0f) : 1.0f;
+#endif
       // mean = sum x (1 / max(deg, 1)) with the correctly rounded reciprocal: at most 1 ulp from the reference's division
       // (models/egnn_utils.py:53-70), and 32 IEEE divisions per thread and chunk were 2.4 k of the 4 k cycles each chunk
       // of the tile's first A operand took (cycle trace)
@@ -542,12 +583,25 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
       // operand (while the first MMAs execute), and all its loads are issued before the first store: written as one
       // load-add-store-store per coordinate it is a chain of 2 D dependent memory round trips (the compiler cannot prove
       // that xagg and xcur do not alias) that sat in front of the tile's first MMA for 20 k cycles (cycle trace).
+#if B200MD_NODE_TS_EARLY_X
+      float xa_early[8], xc_early[8];
+      if (a.do_update && part == 0 && valid) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xa_early[k] = (k < D) ? a.xagg[node * D + k] : 0.f;
+          xc_early[k] = (k < D) ? a.xcur[node * D + k] : 0.f;
+        }
+      }
+#endif
       auto coordinate_update = [&]() {
         if (!(a.do_update && part == 0 && valid)) return;
         for (int d0 = 0; d0 < D; d0 += 8) {
           float xa[8], xc[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
+#if B200MD_NODE_TS_EARLY_X
+            if (d0 == 0) { xa[k] = xa_early[k]; xc[k] = xc_early[k]; continue; }
+#endif
             xa[k] = (d0 + k < D) ? a.xagg[node * D + d0 + k] : 0.f;
             xc[k] = (d0 + k < D) ? a.xcur[node * D + d0 + k] : 0.f;
           }
