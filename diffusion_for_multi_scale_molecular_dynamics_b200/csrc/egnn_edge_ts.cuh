@@ -117,8 +117,8 @@ constexpr int kTsPqStageBytes = kTileM * kTsPqRowBytes;    // 34 KB
 struct TsSmem {
   uint32_t b, seg, qx, q0, pst, pslot, bars, tmem_slot, bias, scale, wr, wlast, dot, total;
 };
-__host__ __device__ inline TsSmem ts_smem(int n_gemms) {
-  TsSmem L;
+__host__ __device__ constexpr TsSmem ts_smem(int n_gemms) {
+  TsSmem L{};
   uint32_t o = 0;
   L.b = o; o += kTsEdgeBStages * kTsEdgeBStageBytes;
   L.seg = o; o += B200MD_TS_SEG_SMEM ? kTsEpiWarps * kTsSegTileBytes : 0;
@@ -138,6 +138,7 @@ __host__ __device__ inline TsSmem ts_smem(int n_gemms) {
   L.total = o;
   return L;
 }
+static_assert(ts_smem(kMaxGemms).total + 1024 <= 227 * 1024, "edge kernel: shared memory (weight ring + segmented-sum tiles + gather ring) beyond 227 KB");
 
 
 // Optional cycle trace of CTA 0 (build with -DB200MD_TS_TRACE; read back with b200md_debug_ts_trace): one record

@@ -155,8 +155,8 @@ constexpr int kNodeStageBytes = 32 * 128;
 struct NodeTsSmem {
   uint32_t b, stage, in, bars, tmem_slot, bias, scale, readout, logits, total;
 };
-__host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
-  NodeTsSmem L;
+__host__ __device__ constexpr NodeTsSmem node_ts_smem(int n_gemms) {
+  NodeTsSmem L{};
   uint32_t o = 0;
   L.b = o; o += kNodeBStages * kTsBStageBytes;
   L.stage = o; o += kTsEpiWarps * kNodeStageBytes;
@@ -171,6 +171,8 @@ __host__ __device__ inline NodeTsSmem node_ts_smem(int n_gemms) {
   L.total = o;
   return L;
 }
+
+static_assert(node_ts_smem(kMaxGemms).total + 1024 <= 227 * 1024, "node kernel: shared memory (weight ring + staging + input ring) beyond 227 KB");
 
 struct NodeTsBars {
   uint32_t bar0;
