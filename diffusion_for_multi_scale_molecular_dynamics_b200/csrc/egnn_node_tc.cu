@@ -7,6 +7,7 @@
 // a tile is 128 consecutive nodes and the program of a call is
 //     [ Linear(H+M -> H) SiLU, n x (Linear(H -> H) SiLU), Linear(H -> H) + residual ]      when a layer is updated
 //     [ Linear(H -> M) -> P,  Linear(H -> M) -> Q ]                                          when another layer follows.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda at link time)
 #include <math_constants.h>
 
 #include "egnn.cuh"
@@ -343,6 +344,33 @@ int tc_node_pack_layer(const b200md_egnn_config& cfg, const EgnnLayout& lay, int
   return B200MD_OK;
 }
 
+#if B200MD_NODE_TS_TMA_STORE
+// Tensor map of a row-major fp32 array [n_rows, ld] for the node kernel's row stores: box = 32 rows x 32 columns (128 bytes),
+// SWIZZLE_128B (the staging tile's XOR pattern), rows beyond n_rows clipped.
+typedef CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int node_row_tensor_map(CUtensorMap* map, float* rows, int64_t n_rows, int ld) {
+  static TensorMapEncodeTiled encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult status;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status) != cudaSuccess ||
+        status != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return (TensorMapEncodeTiled)fn;
+  }();
+  if (encode == nullptr) return set_cuda_error(cudaErrorNotSupported);   // cuTensorMapEncodeTiled is not available from this driver
+  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)(n_rows > 0 ? n_rows : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32u, 32u};
+  const cuuint32_t elem[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, rows, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_cuda_error(cudaErrorInvalidValue);   // the encoder refused the array (alignment, extent)
+  return B200MD_OK;
+}
+#endif
+
 int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const float* packed, const NodeCall& call,
                    int precision, cudaStream_t st) {
   const int H = cfg.node_hidden, M = cfg.message_hidden;
@@ -396,19 +424,19 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
       const EgnnLayerOffsets& Lo = lay.layer[call.update_layer];
       const int64_t base = (int64_t)call.update_layer * lay.tc_node_stride;
       const int64_t w0 = f16(base + im.w0, H + M, H);
-      t.g[n] = NodeTsGemm{M, H, kNodeChainAddU, 1, 0, 0, w0 + (int64_t)(H / 64) * 2 * H * 32, uns(base + im.w0, H + M, H), -1, nullptr}; ++n;
+      t.g[n] = NodeTsGemm{M, H, kNodeChainAddU, 1, 0, 0, w0 + (int64_t)(H / 64) * 2 * H * 32, uns(base + im.w0, H + M, H), -1, nullptr, -1}; ++n;
       for (int i = 0; i < cfg.node_n_hidden; ++i) {
         const int64_t image = base + im.hidden + i * weight_image_floats(H, H);
-        t.g[n] = NodeTsGemm{H, H, kNodeChain, 1, 0, 0, f16(image, H, H), uns(image, H, H), Lo.node_hidden_b + (int64_t)i * H, nullptr}; ++n;
+        t.g[n] = NodeTsGemm{H, H, kNodeChain, 1, 0, 0, f16(image, H, H), uns(image, H, H), Lo.node_hidden_b + (int64_t)i * H, nullptr, -1}; ++n;
       }
-      t.g[n] = NodeTsGemm{H, H, kNodeChainLast, 1, 0, 0, f16(base + im.last, H, H), uns(base + im.last, H, H), Lo.node_last_b, nullptr}; ++n;
+      t.g[n] = NodeTsGemm{H, H, kNodeChainLast, 1, 0, 0, f16(base + im.last, H, H), uns(base + im.last, H, H), Lo.node_last_b, nullptr, -1}; ++n;
     }
     if (call.pq_layer >= 0) {
       const EgnnLayerOffsets& Lo = lay.layer[call.pq_layer];
       const int64_t base = (int64_t)call.pq_layer * lay.tc_node_stride;
-      t.g[n] = NodeTsGemm{H, M, kNodeOut, 1, 0, 1, f16(base + im.wa, H, M), uns(base + im.wa, H, M), Lo.msg_b0, call.ws->P}; ++n;
-      t.g[n] = NodeTsGemm{H, M, kNodeOut, 0, 1, 1, f16(base + im.wb, H, M), uns(base + im.wb, H, M), -1, call.ws->Q}; ++n;
-      t.g[n] = NodeTsGemm{H, H, kNodeOut, 0, 1, 0, f16(base + im.w0, H + M, H), uns(base + im.w0, H + M, H), Lo.node_b0, call.ws->U}; ++n;
+      t.g[n] = NodeTsGemm{H, M, kNodeOut, 1, 0, 1, f16(base + im.wa, H, M), uns(base + im.wa, H, M), Lo.msg_b0, call.ws->P, 1}; ++n;
+      t.g[n] = NodeTsGemm{H, M, kNodeOut, 0, 1, 1, f16(base + im.wb, H, M), uns(base + im.wb, H, M), -1, call.ws->Q, 2}; ++n;
+      t.g[n] = NodeTsGemm{H, H, kNodeOut, 0, 1, 0, f16(base + im.w0, H + M, H), uns(base + im.w0, H + M, H), Lo.node_b0, call.ws->U, 3}; ++n;
     }
     t.n_gemms = n;
     t.do_embed = call.embed; t.do_update = call.update_layer >= 0; t.do_readout = call.readout;
@@ -422,6 +450,18 @@ int tc_launch_node(const b200md_egnn_config& cfg, const EgnnLayout& lay, const f
     t.bloch = lay.bloch; t.proj = lay.proj; t.embed_w = lay.embed_w; t.embed_b = lay.embed_b;
     t.readout_w = lay.readout_w; t.readout_b = lay.readout_b;
     t.trace = (call.update_layer == 1 && call.pq_layer >= 0) ? 1 : 0;
+#if B200MD_NODE_TS_TMA_STORE
+    {
+      const int rc_h = node_row_tensor_map(&t.tm[0], call.ws->h, call.n_nodes, H);
+      if (rc_h != B200MD_OK) return rc_h;
+      if (call.pq_layer >= 0) {
+        int rc_o;
+        if ((rc_o = node_row_tensor_map(&t.tm[1], call.ws->P, call.n_nodes, M)) != B200MD_OK) return rc_o;
+        if ((rc_o = node_row_tensor_map(&t.tm[2], call.ws->Q, call.n_nodes, M)) != B200MD_OK) return rc_o;
+        if ((rc_o = node_row_tensor_map(&t.tm[3], call.ws->U, call.n_nodes, H)) != B200MD_OK) return rc_o;
+      }
+    }
+#endif
     const size_t ts_bytes = node_ts_smem(n).total + 1024;
     static PerDeviceOnce ts_attr_set;
     if (ts_attr_set.needed()) {

@@ -49,6 +49,8 @@ enum NodeGemmKind {
   kNodeOut = 3,         // out[node] = acc + bias                     (P, Q, U)
 };
 
+constexpr int kNodeTensorMaps = 4;   // B200MD_NODE_TS_TMA_STORE: h, and the (at most three) outputs of a call in GEMM order
+
 struct NodeTsGemm {
   int K, N, kind;
   int fresh_a;          // the MMA waits for the epilogue to publish the A chunks (else: same A as the previous GEMM)
@@ -59,9 +61,11 @@ struct NodeTsGemm {
   int64_t unscale;      // offset in wtc of 2^-s: the image holds 2^s w (tc_common.cuh), the epilogue multiplies it back
   int64_t bias;         // offset in packed, or -1
   float* out;           // kNodeOut: destination [n_nodes, N]
+  int tm;               // kNodeOut: index of its tensor map in NodeTsArgs::tm (B200MD_NODE_TS_TMA_STORE)
 };
 
 struct NodeTsArgs {
+  alignas(64) CUtensorMap tm[kNodeTensorMaps];   // [n_nodes, ld] fp32, box 32 x 32, SWIZZLE_128B: 0 = h, 1 .. = the outputs
   const float* wtc;
   const float* packed;
   int n_gemms;
@@ -133,6 +137,21 @@ static_assert(!B200MD_NODE_TS_DRAIN_PIPELINED || (B200MD_NODE_TS_INPUT_WARPS && 
 // output stores, they took 4 - 6 k cycles to arrive (trace r02e).  2: also the next tile's U rows.
 #ifndef B200MD_NODE_TS_L2_AHEAD
 #define B200MD_NODE_TS_L2_AHEAD 0
+#endif
+// B200MD_NODE_TS_TMA_STORE = 1: the rows the epilogue WRITES (h', P, Q, U: 32 rows x 128 bytes per warp and chunk) leave through
+// the TMA: the warp stages its tile exactly as before (XOR-swizzled 16-byte groups = the TMA's SWIZZLE_128B pattern), and one
+// lane issues ONE 2-D tensor store (cp.async.bulk.tensor.2d, SASS UTMASTG) of the 32 x 32 box instead of 8 shared loads and 8
+// global stores per thread; rows beyond the end of the array are clipped by the tensor map.  The store is asynchronous: the
+// warp goes on to the next chunk and only waits (bulk wait_group.read) before it refills the staging tile -- the cycle trace
+// r02e showed 1.2 - 1.5 k of a chunk's 2.6 k cycles in the drain spent behind the back-pressure of the global stores.
+#ifndef B200MD_NODE_TS_STAGGER_GROUPS
+#define B200MD_NODE_TS_STAGGER_GROUPS 1
+#endif
+#ifndef B200MD_NODE_TS_STAGGER_CYCLES
+#define B200MD_NODE_TS_STAGGER_CYCLES 50000
+#endif
+#ifndef B200MD_NODE_TS_TMA_STORE
+#define B200MD_NODE_TS_TMA_STORE 0
 #endif
 constexpr bool kNodeInputWarps = B200MD_NODE_TS_INPUT_WARPS != 0;
 static_assert(!kNodeInputWarps || B200MD_TS_WARPGROUPS, "the input warps are warps 2 and 3 of the control warpgroup");
@@ -213,7 +232,15 @@ __device__ __forceinline__ void store_cols(float* p, const float (&v)[kTsCols]) 
     *reinterpret_cast<float4*>(p + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-__global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeTsArgs a) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_tile, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_tile), "r"(col), "r"(row)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __grid_constant__ NodeTsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const NodeTsSmem L = node_ts_smem(a.n_gemms);
@@ -251,6 +278,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
   tc_fence_after();
   const uint32_t tmem_base_all = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
   const int n_iterations = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+#if B200MD_NODE_TS_STAGGER_GROUPS > 1
+  // Experiment: CTAs start out of phase (group g of G waits g x B200MD_NODE_TS_STAGGER_CYCLES), so that the output drains of
+  // the 148 CTAs -- all tiles take the same time, the CTAs run in lockstep -- do not hit the memory system together.
+  if (n_iterations > 2) {
+    const long long wait_cycles = (long long)(blockIdx.x % B200MD_NODE_TS_STAGGER_GROUPS) * B200MD_NODE_TS_STAGGER_CYCLES;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait_cycles) __nanosleep(256);
+  }
+#endif
 #ifdef B200MD_TS_TRACE
   bool trace_on = false;
   unsigned trace_idx = 0;
@@ -501,8 +537,22 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
 #endif
       };
       // store this lane's row values as columns [col, col + 32) of the warp's rows of `rows`
-      auto rows_store = [&](float* rows, int ld, int col, const float (&v)[kTsCols]) {
-#if B200MD_NODE_TS_COALESCED
+      auto rows_store = [&](float* rows, int ld, int col, const float (&v)[kTsCols], int tm) {
+#if B200MD_NODE_TS_TMA_STORE
+        (void)rows; (void)ld;
+        if (lane == 0) bulk_wait_read();   // this warp's previous store has read the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          sts128(stage + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4), v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+        fence_proxy_async();               // the tile is read by the async proxy
+        __syncwarp();
+        NODE_TRACE(35, col);
+        if (lane == 0 && rows_valid > 0) {
+          tma_store_2d(&a.tm[tm], stage, col, (int)warp_row0);
+          bulk_commit();
+        }
+#elif B200MD_NODE_TS_COALESCED
 #pragma unroll
         for (int p = 0; p < 8; ++p)
           sts128(stage + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4), v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
@@ -629,7 +679,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             const int o = col0 + j;
             v[j] = valid ? Wp[a.embed_b + o] + (Wp[a.embed_w + o * a.F0] * sg + Wp[a.embed_w + o * a.F0 + 1 + atc]) : 0.f;
           }
-          rows_store(a.h, H, col0, v);
+          rows_store(a.h, H, col0, v, 0);
           publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
         }
         for (int c = 0; c < M / 64; ++c) rows_zero(a.agg, M, c * 64 + part * kTsCols);
@@ -814,7 +864,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
             if (becomes_a) publish(d_col + (uint32_t)col0, v, kF16ActScale);   // h' is the A operand of the outputs
             NODE_TRACE(30, g * 16 + c);
             if (G.kind == kNodeChainLast) {
-              rows_store(a.h, H, col0, v);
+              rows_store(a.h, H, col0, v, 0);
               if (a.do_readout) {   // logits = W_c h + b_c (egnn.py:379): partial dot products while h' is in registers
 #pragma unroll
                 for (int cl = 0; cl < kNodeMaxClasses; ++cl)
@@ -830,7 +880,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                   }
               }
             } else {
-              rows_store(G.out, G.N, col0, v);
+              rows_store(G.out, G.N, col0, v, G.tm);
             }
             NODE_TRACE(34, g * 16 + c);
             if (valid) {
@@ -891,7 +941,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
                 for (int j = 0; j < kTsCols; ++j) v[j] = u[j] + v[j];
               }
               NODE_TRACE(33, (g * 16 + c) | ((__float_as_uint(v[0] + v[31]) & 1u) << 20));
-              rows_store(a.h, H, col0, v);
+              rows_store(a.h, H, col0, v, 0);
               NODE_TRACE(34, g * 16 + c);
               if (a.do_readout) {   // logits = W_c h + b_c (egnn.py:379): partial dot products while h' is in registers
 #pragma unroll
@@ -909,7 +959,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
               }
             } else {
               NODE_TRACE(33, (g * 16 + c) | ((__float_as_uint(v[0] + v[31]) & 1u) << 20));
-              rows_store(G.out, G.N, col0, v);
+              rows_store(G.out, G.N, col0, v, G.tm);
               NODE_TRACE(34, g * 16 + c);
             }
             if (valid) {
@@ -966,6 +1016,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const NodeT
     }
 #if B200MD_NODE_TS_PIPELINED
     if (part == 0) sfu_acquire(tok_mine);   // the peer's last release
+#endif
+#if B200MD_NODE_TS_TMA_STORE
+    if (lane == 0) bulk_wait_all();   // the staging tiles have been read and the rows written before the CTA goes away
 #endif
     if (!(fabsf(checksum) <= CUDART_MAX_NORMAL_F)) local_status |= B200MD_STATUS_TC_RANGE;
     if (local_status && a.status) atomicOr(a.status, (int)local_status);
