@@ -144,6 +144,9 @@ static_assert(!B200MD_NODE_TS_DRAIN_PIPELINED || (B200MD_NODE_TS_INPUT_WARPS && 
 // global stores per thread; rows beyond the end of the array are clipped by the tensor map.  The store is asynchronous: the
 // warp goes on to the next chunk and only waits (bulk wait_group.read) before it refills the staging tile -- the cycle trace
 // r02e showed 1.2 - 1.5 k of a chunk's 2.6 k cycles in the drain spent behind the back-pressure of the global stores.
+#ifndef B200MD_NODE_TS_LATE_ZERO
+#define B200MD_NODE_TS_LATE_ZERO 0
+#endif
 #ifndef B200MD_NODE_TS_STAGGER_GROUPS
 #define B200MD_NODE_TS_STAGGER_GROUPS 1
 #endif
@@ -708,11 +711,19 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
             for (int j = 0; j < kTsCols; ++j) v[j] = B200MD_NODE_TS_EXACT_DIV ? v[j] / degf : v[j] * inv_deg;
           }
           NODE_TRACE(24, c);
+#if !B200MD_NODE_TS_LATE_ZERO
           rows_zero(a.agg, M, col0);
+#endif
           NODE_TRACE(25, c);
           publish(a_col0 + (uint32_t)col0, v, kF16ActScale);
           NODE_TRACE(21, c);
         }
+#if B200MD_NODE_TS_LATE_ZERO
+        // the reset of the agg rows waits until the whole A operand is out: issued chunk by chunk, its 32 KB of stores per
+        // chunk sat in the SM's memory queue in front of the input warps' requests for chunks 2 and 3 (4 - 6 k cycles from
+        // request to arrival in the trace r02e); here they drain while the first GEMM runs
+        for (int c = 0; c < M / 64; ++c) rows_zero(a.agg, M, c * 64 + part * kTsCols);
+#endif
       }
       coordinate_update();
 
