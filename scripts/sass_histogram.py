@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
     ROOT, "diffusion_for_multi_scale_molecular_dynamics_b200", "csrc", "libb200md.so")
-WATCH = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "SYNCS", "MUFU", "RED", "REDG", "ATOM", "ATOMG", "ATOMS", "BAR",
+WATCH = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "UTMASTG", "LDGSTS", "ARRIVES", "SYNCS", "MUFU", "RED", "REDG", "ATOM", "ATOMG", "ATOMS", "BAR",
          "FFMA", "FFMA2", "FMUL2", "FADD2", "HFMA2", "LDG", "STG", "LDS", "STS", "SHFL", "USETMAXREG", "ELECT"]
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
