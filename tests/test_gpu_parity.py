@@ -622,6 +622,31 @@ def test_production_kernels_many_tiles_against_oracle(cuda_device, num_atom_type
     assert net.last_number_of_edges() > 128 * 300
 
 
+def test_later_tiles_of_a_persistent_node_cta_against_oracle(cuda_device):
+    """320 x SiGe 2x2x2 = 20480 nodes = 160 node tiles on 148 persistent CTAs: CTAs 0 .. 11 run a SECOND tile (tiles
+    148 .. 159 = structures 296 .. 319), whose first `agg` chunks were staged by the input warps while the first tile's
+    outputs were still being drained, whose degree was loaded a tile ahead, and whose rows leave through staging tiles the
+    first tile has used.  The oracle (fp32 and fp64) is evaluated on exactly those structures -- structures are
+    independent -- and on the first ones, which share their CTAs."""
+    hp = dict(num_atom_types=2, **PRODUCTION)
+    torch.manual_seed(23)
+    net = EGNNScoreNetwork(EGNNScoreNetworkParameters(**hp))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(cuda_device)
+    B, N = 320, 64
+    x = torch.rand(B, N, 3)
+    a = torch.randint(0, 3, (B, N))
+    lattice = torch.zeros(B, 6)
+    lattice[:, :3] = 11.084
+    sigma = torch.rand(B, 1) * 0.4 + 0.005
+    out = net(network_batch(a, x, lattice, sigma, cuda_device), conditional=False)
+    assert "egnn_edge_ts_kernel" in net.last_edge_kernel_name()
+    for rows in (slice(296, 320), slice(0, 12)):
+        logits32, score32, logits64, score64 = oracle_forward_both(sd, hp, a[rows], x[rows], lattice[rows], sigma[rows])
+        assert_anchored(out.X[rows], score32, score64, f"score of structures {rows.start}..{rows.stop}")
+        assert_anchored(out.A[rows], logits32, logits64, f"logits of structures {rows.start}..{rows.stop}")
+
+
 def test_tcgen05_unsupported_configuration_is_refused(cuda_device):
     g = sub_dict(load_golden("egnn_forward"), "default_fc")  # message width 16: not a multiple of 32
     net = make_network("default_fc", sub_dict(g, "sd"), cuda_device)
