@@ -379,8 +379,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
     const uint32_t b_ring = s_base + L.b;
     const bool leader = elect_one();
     uint32_t cb = 0, mca = 0, abuf = 0, df = 0;
-    uint32_t use0 = 0, use1 = 0;   // completed uses of each accumulator buffer (phase of its acc_full barriers): unused here
-    (void)use0; (void)use1;
     for (int it = 0; it < n_iterations; ++it)
       for (int g = 0; g < a.n_gemms; ++g) {
 #ifdef B200MD_TS_TRACE
@@ -501,6 +499,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
       const int64_t warp_row0 = (int64_t)tile * kTileM + q * 32;   // node of lane 0's row
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.n_nodes - warp_row0));   // warp-uniform
       const int crow = lane >> 3, cpiece = lane & 7;   // cooperative role: instruction i covers rows 4 i + crow, piece cpiece
+#if !B200MD_NODE_TS_INPUT_WARPS   // (with the input warps the epilogue reads its rows from the shared-memory ring: input_collect)
       struct RowTile { float4 p[8]; };
       // request columns [col, col + 32) of the warp's 32 rows of `rows` (row stride ld floats) ...
       auto rows_request = [&](const float* rows, int ld, int col, RowTile& t) {
@@ -539,6 +538,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
         for (int p = 0; p < 8; ++p) { v[4 * p] = t.p[p].x; v[4 * p + 1] = t.p[p].y; v[4 * p + 2] = t.p[p].z; v[4 * p + 3] = t.p[p].w; }
 #endif
       };
+#endif
       // store this lane's row values as columns [col, col + 32) of the warp's rows of `rows`
       auto rows_store = [&](float* rows, int ld, int col, const float (&v)[kTsCols], int tm) {
 #if B200MD_NODE_TS_TMA_STORE
@@ -784,7 +784,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
                                  v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dep);
               }
             } else {
-#pragma unroll
               float side[kTsCols];
               NODE_TRACE(26, g * 16 + c);
 #if B200MD_NODE_TS_INPUT_WARPS
@@ -905,7 +904,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
           if (becomes_a) abuf ^= 1u;
           continue;
         }
-#endif
+#else
         for (int c = 0; c < nchunks; ++c) {
           wait_for_chunk(c);
           const int col0 = c * 64 + part * kTsCols;
@@ -995,6 +994,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) egnn_node_ts_kernel(const __gri
         }
         ++uses[dbuf];
         if (becomes_a) abuf ^= 1u;
+#endif
       }
 
       if (a.do_readout) {
